@@ -1,0 +1,10 @@
+"""asr_chinese_e2e_b200 -- B200-native CTC loss+grad hot path for zqs01/ASR_chinese_e2e.
+
+Public surface: ``ctc_loss_b200`` / ``CTCLossB200`` (the op), ``JointCTCAttention`` (model-side
+glue for ``TransformerOffical.cal_metrics``), ``sharded_ctc_loss`` (batch-sharded multi-GPU loss).
+Importing the package does not load the CUDA library; the first call does, and raises if
+libctcb200.so is missing -- there is no CPU fallback.
+"""
+from .ctc import CTCLossB200, ctc_loss_b200  # noqa: F401
+
+__all__ = ["CTCLossB200", "ctc_loss_b200"]

@@ -1,0 +1,92 @@
+"""Loader (and in-tree builder) of libctcb200.so, the C-ABI CUDA library (include/ctcb200.h).
+
+There is exactly one implementation of the hot path: hand-written sm_100a kernels.  If the
+shared library is missing or cannot be loaded this module raises -- there is no CPU or
+PyTorch fallback (BASELINE.json north_star).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+SO_PATH = os.path.join(_HERE, "libctcb200.so")
+SOURCES = ["ctcb200.cu"]
+HEADERS = ["ptx.cuh", "layout.h", "stream_kernels.cuh", "lattice_kernel.cuh",
+           os.path.join("..", "..", "include", "ctcb200.h")]
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    return any(os.path.getmtime(os.path.join(_CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a -> asr_chinese_e2e_b200/libctcb200.so (in-tree)."""
+    if not force and not needs_build():
+        return SO_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", SO_PATH] + [os.path.join(_CSRC, s) for s in SOURCES]
+    subprocess.check_call(cmd)
+    return SO_PATH
+
+
+class CtcB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+_i, _i64, _sz, _f, _p = ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_float, ctypes.c_void_p
+
+_FWD_ARGS = [_p, _p, _i64, _i64, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]
+SIGNATURES = {
+    "ctcb200_version": (_i, []),
+    "ctcb200_strerror": (ctypes.c_char_p, [_i]),
+    "ctcb200_workspace_bytes": (_i, [_i, _i, _i, _i, ctypes.POINTER(_sz)]),
+    "ctcb200_forward": (_i, _FWD_ARGS),
+    "ctcb200_loss_only": (_i, _FWD_ARGS),
+    "ctcb200_backward": (_i, [_p, _p, _i64, _i64, _p, _i64, _i, _f, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "ctcb200_read_status": (_i, [_p, ctypes.POINTER(_i), _p]),
+}
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise CtcB200Error(
+                f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback for the CTC hot path.")
+        try:
+            handle = ctypes.CDLL(SO_PATH)
+        except OSError as e:  # pragma: no cover
+            raise CtcB200Error(f"cannot load {SO_PATH}: {e}") from e
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def strerror(code: int) -> str:
+    return lib().ctcb200_strerror(int(code)).decode()
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        raise CtcB200Error(f"{what} failed: [{code}] {strerror(code)}")
+
+
+def workspace_bytes(B: int, T: int, V: int, Umax: int) -> int:
+    out = _sz(0)
+    check(lib().ctcb200_workspace_bytes(B, T, V, Umax, ctypes.byref(out)), "ctcb200_workspace_bytes")
+    return int(out.value)

@@ -1,0 +1,256 @@
+// C-ABI of libctcb200.so (declared in include/ctcb200.h): argument validation, workspace
+// carve-up, launch configuration.  All device work is asynchronous on the caller's stream.
+#include "../../include/ctcb200.h"
+
+#include <cuda_runtime.h>
+#include <stdlib.h>
+
+#include "lattice_kernel.cuh"
+#include "layout.h"
+#include "stream_kernels.cuh"
+
+using namespace ctcb200;
+
+namespace {
+
+constexpr int kMaxV = 16384;
+constexpr size_t kSmemBudget = 226 * 1024;   // leave 1 KB of the 227 KB opt-in limit to the driver
+
+int env_int(const char *name, int dflt) {
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+struct DevInfo {
+    int sms;
+    int cc_major;
+};
+int device_info(DevInfo *d) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return CTCB200_ERR_NO_DEVICE;
+    if (cudaDeviceGetAttribute(&d->sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&d->cc_major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+        return CTCB200_ERR_NO_DEVICE;
+    if (d->cc_major != 10) return CTCB200_ERR_NO_DEVICE;   // sm_100a SASS only: no other path exists
+    return 0;
+}
+
+int check_common(const void *logits, const void *targets, const void *in_len, const void *tgt_len,
+                 int B, int T, int V, int Umax, int blank, const void *workspace, size_t ws_bytes,
+                 Geom *g, Workspace *w) {
+    if (B < 0 || T < 1 || V < 2 || V > kMaxV) return CTCB200_ERR_SHAPE;
+    if (blank < 0 || blank >= V) return CTCB200_ERR_BLANK;
+    if (!geom_for(Umax, g)) return CTCB200_ERR_UMAX;
+    if (!logits || !targets || !in_len || !tgt_len || !workspace) return CTCB200_ERR_NULL;
+    if (((uintptr_t)logits & 15) || ((uintptr_t)workspace & 255)) return CTCB200_ERR_ALIGN;
+    *w = workspace_layout(B, T, *g);
+    if (ws_bytes < w->total) return CTCB200_ERR_WORKSPACE;
+    return 0;
+}
+
+struct StreamCfg {
+    int nst;
+    uint32_t slot_bytes, stage_bytes;
+    size_t smem;
+    int grid;
+};
+// ring geometry of the two sweep kernels; extra = bytes appended to every stage / fixed tail
+int stream_cfg(int V, int Lp, uint32_t stage_extra, size_t fixed_extra, int sms, const char *env_nst,
+               const char *env_cps, StreamCfg *c) {
+    c->slot_bytes = (uint32_t)align_up((size_t)V * 4 + 32, 128);
+    c->stage_bytes = c->slot_bytes + stage_extra;
+    int nst = env_int(env_nst, 3);
+    if (nst < 2) nst = 2;
+    if (nst > 8) nst = 8;
+    while (nst > 2 && (size_t)nst * c->stage_bytes + fixed_extra + 8 * nst > kSmemBudget) --nst;
+    c->nst = nst;
+    c->smem = (size_t)nst * c->stage_bytes + 8 * nst + fixed_extra;
+    if (c->smem > kSmemBudget) return CTCB200_ERR_SHAPE;
+    int cps = (int)(kSmemBudget / (c->smem + 1024));   // + per-CTA reserved shared memory
+    if (cps > 4) cps = 4;
+    if (cps < 1) cps = 1;
+    cps = env_int(env_cps, cps);
+    if (cps < 1) cps = 1;
+    c->grid = sms * cps;
+    (void)Lp;
+    return 0;
+}
+
+template <int MAXC>
+cudaError_t launch_k1(const StreamCfg &c, cudaStream_t s, const float *logits, const int64_t *targets,
+                      int64_t tnumel, const int *Tb, const int *Ub, const int64_t *toff, const int *rowstart,
+                      float *lp_lab, int *hdr, int B, int T, int V, int Lp, int blank) {
+    cudaError_t e = cudaFuncSetAttribute(k1_lse_gather<MAXC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)c.smem);
+    if (e != cudaSuccess) return e;
+    k1_lse_gather<MAXC><<<c.grid, kStreamThreads, c.smem, s>>>(logits, targets, tnumel, Tb, Ub, toff, rowstart,
+                                                               lp_lab, hdr, B, T, V, Lp, blank, c.nst,
+                                                               c.slot_bytes);
+    return cudaGetLastError();
+}
+
+template <int NS, bool GRAD>
+cudaError_t launch_k2(cudaStream_t s, const int64_t *targets, int64_t tnumel, const int *Tb, const int *Ub,
+                      const int64_t *toff, int *flags, const float *lp_lab, float *gam, float *ab, float *nll,
+                      float *loss_sums, unsigned *ticket, int B, int T, int zero_inf) {
+    using C = LatCfg<NS, GRAD>;
+    cudaError_t e = cudaFuncSetAttribute(k2_lattice<NS, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)C::SMEM);
+    if (e != cudaSuccess) return e;
+    k2_lattice<NS, GRAD><<<B, 64, C::SMEM, s>>>(targets, tnumel, Tb, Ub, toff, flags, lp_lab, gam, ab, nll,
+                                                loss_sums, ticket, B, T, zero_inf);
+    return cudaGetLastError();
+}
+
+int forward_impl(bool want_grad, const float *logits, const int64_t *targets, int64_t targets_stride,
+                 int64_t targets_numel, const int64_t *in_len, const int64_t *tgt_len, int B, int T, int V,
+                 int Umax, int blank, int zero_infinity, float *nll, float *loss_sums, void *workspace,
+                 size_t workspace_bytes, ctcb200_stream_t stream) {
+    Geom g;
+    Workspace w;
+    int rc = check_common(logits, targets, in_len, tgt_len, B, T, V, Umax, blank, workspace, workspace_bytes,
+                          &g, &w);
+    if (rc) return rc;
+    if (!nll) return CTCB200_ERR_NULL;
+    if (targets_stride < 0 || targets_numel < 0) return CTCB200_ERR_SHAPE;
+    if (B == 0) return CTCB200_OK;
+    DevInfo dev;
+    if ((rc = device_info(&dev))) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned char *ws = (unsigned char *)workspace;
+    int *hdr = (int *)(ws + w.hdr);
+    int *Tb = (int *)(ws + w.Tb), *Ub = (int *)(ws + w.Ub), *flags = (int *)(ws + w.flags);
+    int64_t *toff = (int64_t *)(ws + w.toff);
+    int *rowstart = (int *)(ws + w.rowstart);
+    float *lp_lab = (float *)(ws + w.lp_lab), *gam = (float *)(ws + w.gam), *ab = (float *)(ws + w.ab);
+    const int64_t tnumel = targets_stride ? (int64_t)B * targets_stride : targets_numel;
+
+    k0_prep<<<1, 1024, 0, s>>>(in_len, tgt_len, targets_stride, B, T, Umax, hdr, Tb, Ub, flags, toff, rowstart);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+
+    StreamCfg c;
+    if ((rc = stream_cfg(V, g.Lp, 0, 64 + (size_t)g.Lp * 4, dev.sms, "CTCB200_K1_NST", "CTCB200_K1_CPS", &c)))
+        return rc;
+    const int nch_max = (V + 6) >> 2;
+    const int maxc = (nch_max + kStreamThreads - 1) / kStreamThreads;
+#define K1_ARGS c, s, logits, targets, tnumel, Tb, Ub, toff, rowstart, lp_lab, hdr, B, T, V, g.Lp, blank
+    if (maxc <= 2) e = launch_k1<2>(K1_ARGS);
+    else if (maxc <= 5) e = launch_k1<5>(K1_ARGS);
+    else if (maxc <= 9) e = launch_k1<9>(K1_ARGS);
+    else if (maxc <= 17) e = launch_k1<17>(K1_ARGS);
+    else e = launch_k1<33>(K1_ARGS);
+#undef K1_ARGS
+    if (e != cudaSuccess) return (int)e;
+
+    unsigned *ticket = (unsigned *)(hdr + 1);
+#define K2_ARGS s, targets, tnumel, Tb, Ub, toff, flags, lp_lab, gam, ab, nll, loss_sums, ticket, B, T, zero_infinity
+    if (want_grad) {
+        if (g.NS == 4) e = launch_k2<4, true>(K2_ARGS);
+        else if (g.NS == 8) e = launch_k2<8, true>(K2_ARGS);
+        else e = launch_k2<16, true>(K2_ARGS);
+    } else {
+        if (g.NS == 4) e = launch_k2<4, false>(K2_ARGS);
+        else if (g.NS == 8) e = launch_k2<8, false>(K2_ARGS);
+        else e = launch_k2<16, false>(K2_ARGS);
+    }
+#undef K2_ARGS
+    return (int)e;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ctcb200_version(void) { return CTCB200_VERSION; }
+
+const char *ctcb200_strerror(int code) {
+    switch (code) {
+        case CTCB200_OK: return "ok";
+        case CTCB200_ERR_NULL: return "required pointer is NULL";
+        case CTCB200_ERR_SHAPE: return "bad shape (need B>=0, T>=1, 2<=V<=16384, strides>=0)";
+        case CTCB200_ERR_BLANK: return "blank index outside [0,V)";
+        case CTCB200_ERR_UMAX: return "Umax outside [0,255]";
+        case CTCB200_ERR_ALIGN: return "logits/grad must be 16-byte aligned, workspace 256-byte aligned";
+        case CTCB200_ERR_REDUCTION: return "unknown reduction code";
+        case CTCB200_ERR_WORKSPACE: return "workspace too small (see ctcb200_workspace_bytes)";
+        case CTCB200_ERR_NO_DEVICE: return "no CUDA device with compute capability 10.x (sm_100a) is current";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "unknown ctcb200 error";
+}
+
+int ctcb200_workspace_bytes(int B, int T, int V, int Umax, size_t *out_bytes) {
+    if (!out_bytes) return CTCB200_ERR_NULL;
+    if (B < 0 || T < 1 || V < 2 || V > kMaxV) return CTCB200_ERR_SHAPE;
+    Geom g;
+    if (!geom_for(Umax, &g)) return CTCB200_ERR_UMAX;
+    *out_bytes = workspace_layout(B, T, g).total;
+    return CTCB200_OK;
+}
+
+int ctcb200_forward(const float *logits, const int64_t *targets, int64_t targets_stride, int64_t targets_numel,
+                    const int64_t *in_len, const int64_t *tgt_len, int B, int T, int V, int Umax, int blank,
+                    int zero_infinity, float *nll, float *loss_sums, void *workspace, size_t workspace_bytes,
+                    ctcb200_stream_t stream) {
+    return forward_impl(true, logits, targets, targets_stride, targets_numel, in_len, tgt_len, B, T, V, Umax,
+                        blank, zero_infinity, nll, loss_sums, workspace, workspace_bytes, stream);
+}
+
+int ctcb200_loss_only(const float *logits, const int64_t *targets, int64_t targets_stride, int64_t targets_numel,
+                      const int64_t *in_len, const int64_t *tgt_len, int B, int T, int V, int Umax, int blank,
+                      int zero_infinity, float *nll, float *loss_sums, void *workspace, size_t workspace_bytes,
+                      ctcb200_stream_t stream) {
+    return forward_impl(false, logits, targets, targets_stride, targets_numel, in_len, tgt_len, B, T, V, Umax,
+                        blank, zero_infinity, nll, loss_sums, workspace, workspace_bytes, stream);
+}
+
+int ctcb200_backward(const float *logits, const int64_t *targets, int64_t targets_stride, int64_t targets_numel,
+                     const float *grad_out, int64_t grad_out_stride, int reduction, float inv_batch, int B,
+                     int T, int V, int Umax, int blank, int zero_infinity, float *grad_logits,
+                     const void *workspace, size_t workspace_bytes, ctcb200_stream_t stream) {
+    Geom g;
+    Workspace w;
+    // in_len/tgt_len are not re-read: the clamped copies of the forward live in the workspace
+    int rc = check_common(logits, targets, workspace, workspace, B, T, V, Umax, blank, workspace, workspace_bytes,
+                          &g, &w);
+    if (rc) return rc;
+    if (!grad_out || !grad_logits) return CTCB200_ERR_NULL;
+    if ((uintptr_t)grad_logits & 15) return CTCB200_ERR_ALIGN;
+    if (reduction < 0 || reduction > 2) return CTCB200_ERR_REDUCTION;
+    if (targets_stride < 0 || targets_numel < 0 || grad_out_stride < 0) return CTCB200_ERR_SHAPE;
+    if (B == 0) return CTCB200_OK;
+    DevInfo dev;
+    if ((rc = device_info(&dev))) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned char *ws = (const unsigned char *)workspace;
+    const int *Tb = (const int *)(ws + w.Tb), *Ub = (const int *)(ws + w.Ub), *flags = (const int *)(ws + w.flags);
+    const int64_t *toff = (const int64_t *)(ws + w.toff);
+    const int *rowstart = (const int *)(ws + w.rowstart);
+    const float *gam = (const float *)(ws + w.gam);
+    const int64_t tnumel = targets_stride ? (int64_t)B * targets_stride : targets_numel;
+
+    StreamCfg c;
+    const uint32_t gam_stage = (uint32_t)align_up((size_t)g.Lp * 4, 128);
+    if ((rc = stream_cfg(V, g.Lp, gam_stage, 3 * (size_t)g.Lp * 4, dev.sms, "CTCB200_K3_NST", "CTCB200_K3_CPS", &c)))
+        return rc;
+    cudaError_t e = cudaFuncSetAttribute(k3_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+    if (e != cudaSuccess) return (int)e;
+    k3_grad<<<c.grid, kStreamThreads, c.smem, s>>>(logits, targets, tnumel, Tb, Ub, toff, flags, rowstart, gam,
+                                                   grad_out, grad_out_stride, reduction, inv_batch, grad_logits,
+                                                   B, T, V, g.Lp, blank, zero_infinity, c.nst, c.slot_bytes,
+                                                   c.stage_bytes);
+    return (int)cudaGetLastError();
+}
+
+int ctcb200_read_status(const void *workspace, int *host_status, ctcb200_stream_t stream) {
+    if (!workspace || !host_status) return CTCB200_ERR_NULL;
+    cudaError_t e = cudaMemcpyAsync(host_status, workspace, sizeof(int), cudaMemcpyDeviceToHost,
+                                    (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaStreamSynchronize((cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,67 @@
+// Geometry and HBM workspace layout shared by host launchers and kernels.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+namespace ctcb200 {
+
+// The lattice kernel gives each lane NS consecutive blank-extended states (NS/2 labels);
+// one warp covers S = 2U+1 <= 32*NS states.  NS is picked from Umax.
+struct Geom {
+    int NS;  // states per lane: 4, 8 or 16
+    int Lp;  // floats per (b,t) frame of lp_lab / gam: 4 header + 16*NS label slots
+    int Sp;  // floats per (b,t) row of the stored alpha/beta halves: 32*NS
+};
+
+static inline bool geom_for(int Umax, Geom *g) {
+    int NS;
+    if (Umax < 0) return false;
+    if (Umax <= 63) NS = 4;
+    else if (Umax <= 127) NS = 8;
+    else if (Umax <= 255) NS = 16;
+    else return false;
+    g->NS = NS;
+    g->Lp = 4 + 16 * NS;
+    g->Sp = 32 * NS;
+    return true;
+}
+
+// Frame layout (floats), log2 units:  [0] blank, [1] lse2 of the frame, [2..3] unused,
+// [4+j] label slot j (j < U_b; -inf beyond).  In `gam` the same slots hold the posterior
+// state occupancies: [0] sum over all blank states, [4+j] label state of slot j.
+
+constexpr size_t kAlign = 256;
+static inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a; }
+
+struct Workspace {
+    // byte offsets from the workspace base
+    size_t hdr;       // int status; unsigned ticket; (256 B)
+    size_t Tb;        // int[B]   clamped input lengths
+    size_t Ub;        // int[B]   clamped target lengths
+    size_t flags;     // int[B]   1 = infeasible (no valid alignment)
+    size_t toff;      // int64[B] element offset of utterance b's labels in `targets`
+    size_t rowstart;  // int[B+1] exclusive prefix sum of Tb (valid-frame numbering)
+    size_t lp_lab;    // float[B*T*Lp]
+    size_t gam;       // float[B*T*Lp]
+    size_t ab;        // float[B*T*Sp]
+    size_t total;
+};
+
+static inline Workspace workspace_layout(int B, int T, const Geom &g) {
+    Workspace w;
+    size_t o = 0;
+    const size_t b = (size_t)(B > 0 ? B : 1);
+    w.hdr = o;       o += kAlign;
+    w.Tb = o;        o += align_up(sizeof(int) * b);
+    w.Ub = o;        o += align_up(sizeof(int) * b);
+    w.flags = o;     o += align_up(sizeof(int) * b);
+    w.toff = o;      o += align_up(sizeof(int64_t) * b);
+    w.rowstart = o;  o += align_up(sizeof(int) * (b + 1));
+    w.lp_lab = o;    o += align_up(sizeof(float) * b * T * g.Lp);
+    w.gam = o;       o += align_up(sizeof(float) * b * T * g.Lp);
+    w.ab = o;        o += align_up(sizeof(float) * b * T * g.Sp);
+    w.total = o;
+    return w;
+}
+
+}  // namespace ctcb200

@@ -1,0 +1,446 @@
+// Streaming kernels of the CTC hot path (HBM-bound):
+//   k0_prep        lengths -> clamped lengths, label offsets, valid-frame prefix sums
+//   k1_lse_gather  ONE read sweep of the valid logits frames: per-frame log-sum-exp and the
+//                  (U+1) label log-probs the lattice needs            (replaces aten::_log_softmax)
+//   k3_grad        second read of the valid frames + the write of grad[B,T,V]:
+//                  g_b * (softmax - occupancy), zeros for padded frames
+//                  (replaces aten::_ctc_loss_backward collect + _log_softmax_backward_data)
+//
+// Both sweeps are persistent CTAs (a few per SM) that own a contiguous run of frames and keep a
+// ring of whole logits rows in shared memory, filled by 1-D bulk TMA copies (cp.async.bulk ->
+// UBLKCP) that complete on mbarriers.  A logits row is V*4 bytes and generally NOT 16-byte aligned
+// (V=4234 -> odd rows start at +8), so each copy covers the 16-byte-aligned hull of the row and the
+// row sits in its slot at the same offset mod 16 as in global memory: float4 smem reads then map
+// one-to-one onto 16-byte-aligned global float4 stores of the gradient.
+#pragma once
+#include "layout.h"
+#include "ptx.cuh"
+
+namespace ctcb200 {
+
+constexpr int kStreamThreads = 128;
+constexpr int kStreamWarps = kStreamThreads / 32;
+
+// ------------------------------------------------------------------------------------------------
+// k0: one CTA.  Clamp/validate lengths, exclusive scans for rowstart[] and (1-D targets) toff[].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k0_prep(const int64_t *__restrict__ in_len,
+                                                const int64_t *__restrict__ tgt_len,
+                                                int64_t targets_stride, int B, int T, int Umax,
+                                                int *__restrict__ hdr, int *__restrict__ Tb_arr,
+                                                int *__restrict__ Ub_arr, int *__restrict__ flags,
+                                                int64_t *__restrict__ toff, int *__restrict__ rowstart) {
+    __shared__ long long s_part[2][32];
+    __shared__ long long s_carry[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { hdr[0] = 0; hdr[1] = 0; s_carry[0] = 0; s_carry[1] = 0; }
+    __syncthreads();
+    int bad = 0;
+    for (int base = 0; base < B; base += 1024) {
+        const int b = base + tid;
+        long long tb = 0, ub = 0;
+        if (b < B) {
+            long long t = in_len[b], u = tgt_len[b];
+            if (t < 0 || t > T) { bad |= 1; t = t < 0 ? 0 : T; }
+            if (u < 0 || u > Umax) { bad |= 2; u = u < 0 ? 0 : Umax; }
+            tb = t; ub = u;
+            Tb_arr[b] = (int)t; Ub_arr[b] = (int)u; flags[b] = 0;
+        }
+        // block-wide inclusive scan of (tb, ub)
+        long long st = tb, su = ub;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long a = __shfl_up_sync(0xffffffffu, st, o), c = __shfl_up_sync(0xffffffffu, su, o);
+            if (lane >= o) { st += a; su += c; }
+        }
+        if (lane == 31) { s_part[0][warp] = st; s_part[1][warp] = su; }
+        __syncthreads();
+        if (warp == 0) {
+            long long pt = s_part[0][lane], pu = s_part[1][lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                long long a = __shfl_up_sync(0xffffffffu, pt, o), c = __shfl_up_sync(0xffffffffu, pu, o);
+                if (lane >= o) { pt += a; pu += c; }
+            }
+            s_part[0][lane] = pt; s_part[1][lane] = pu;   // inclusive over warps
+        }
+        __syncthreads();
+        const long long wt = warp ? s_part[0][warp - 1] : 0, wu = warp ? s_part[1][warp - 1] : 0;
+        const long long ct = s_carry[0], cu = s_carry[1];
+        if (b < B) {
+            rowstart[b] = (int)(ct + wt + st - tb);
+            toff[b] = targets_stride ? (long long)b * targets_stride : (cu + wu + su - ub);
+        }
+        __syncthreads();
+        if (tid == 1023) { s_carry[0] = ct + wt + st; s_carry[1] = cu + wu + su; }
+        __syncthreads();
+    }
+    if (tid == 0) rowstart[B] = (int)s_carry[0];
+    if (bad) atomicOr(&hdr[0], bad);
+}
+
+// ------------------------------------------------------------------------------------------------
+// valid-frame cursor: flattened index over frames t < Tb[b]  <->  (b, t)
+// ------------------------------------------------------------------------------------------------
+struct RowCursor {
+    int b, t, Tb;
+};
+__device__ __forceinline__ void cursor_seek(RowCursor &c, int row, const int *__restrict__ rowstart,
+                                            const int *__restrict__ Tb_arr, int B) {
+    int lo = 0, hi = B - 1;   // smallest b with rowstart[b+1] > row
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (rowstart[mid + 1] > row) hi = mid; else lo = mid + 1;
+    }
+    c.b = lo; c.t = row - rowstart[lo]; c.Tb = Tb_arr[lo];
+}
+__device__ __forceinline__ void cursor_next(RowCursor &c, const int *__restrict__ Tb_arr, int B) {
+    c.t++;
+    while (c.t >= c.Tb && c.b + 1 < B) { c.b++; c.t = 0; c.Tb = Tb_arr[c.b]; }
+}
+
+// Issue the TMA copy of one logits row (its 16-byte hull) into a ring slot.  Called by ONE thread.
+// `end16`: tensor end rounded down to 16; the (at most 3) floats of the very last row that lie past
+// it are fetched with plain loads so that nothing beyond the caller's buffer is ever read.
+__device__ __forceinline__ uint32_t issue_row(const float *row, int V, uintptr_t end16, uint32_t slot,
+                                              uint32_t bar, uint32_t extra_tx) {
+    const uintptr_t a = (uintptr_t)row, a0 = a & ~(uintptr_t)15;
+    uintptr_t a1 = (a + (uintptr_t)V * 4 + 15) & ~(uintptr_t)15;
+    if (a1 > end16) {
+        for (uintptr_t p = (end16 > a ? end16 : a); p < a + (uintptr_t)V * 4; p += 4) {
+            const float v = *(const float *)p;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot + (uint32_t)(p - a0)), "f"(v) : "memory");
+        }
+        a1 = end16 > a0 ? end16 : a0;
+    }
+    const uint32_t bytes = (uint32_t)(a1 - a0);
+    if (bytes + extra_tx) mbar_expect_tx(bar, bytes + extra_tx); else mbar_arrive(bar);
+    if (bytes) tma_load_1d(slot, (const void *)a0, bytes, bar);
+    return bytes;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k1: fused log-softmax statistics + label gather.  One read of each valid frame.
+//   lp_lab[b,t,0] = lp2(blank)   lp_lab[b,t,1] = lse2   lp_lab[b,t,4+j] = lp2(label_j)  (log2 units)
+// MAXC = float4 chunks a thread keeps in registers (128 threads x MAXC x 4 floats >= V + 3).
+// ------------------------------------------------------------------------------------------------
+template <int MAXC>
+__global__ void __launch_bounds__(kStreamThreads)
+k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targets, int64_t tnumel,
+              const int *__restrict__ Tb_arr, const int *__restrict__ Ub_arr,
+              const int64_t *__restrict__ toff_arr, const int *__restrict__ rowstart,
+              float *__restrict__ lp_lab, int *__restrict__ hdr, int B, int T, int V, int Lp, int blank,
+              int nst, uint32_t slot_bytes) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int R = rowstart[B];
+    const int r0 = (int)((long long)R * blockIdx.x / gridDim.x);
+    const int r1 = (int)((long long)R * (blockIdx.x + 1) / gridDim.x);
+    const int nrows = r1 - r0;
+    if (nrows <= 0) return;
+
+    uint64_t *bars = (uint64_t *)(smem + (size_t)nst * slot_bytes);
+    float *red = (float *)(bars + nst);              // [2 parity][2 max/sum][4 warps]
+    int *cls_s = (int *)(red + 16);                  // [Lp] class id per frame slot
+    const uint32_t slot0 = smem_u32(smem), bar0 = smem_u32(bars);
+    if (tid == 0) {
+        for (int s = 0; s < nst; ++s) mbar_init(bar0 + 8 * s, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const uintptr_t end16 = ((uintptr_t)logits + (size_t)B * T * V * 4) & ~(uintptr_t)15;
+    RowCursor pc, cc;
+    cursor_seek(cc, r0, rowstart, Tb_arr, B);
+    pc = cc;
+    int issued = 0;
+    if (tid == 0) {
+        for (; issued < nst && issued < nrows; ++issued) {
+            issue_row(logits + ((size_t)pc.b * T + pc.t) * V, V, end16, slot0 + issued * slot_bytes,
+                      bar0 + 8 * issued, 0);
+            cursor_next(pc, Tb_arr, B);
+        }
+    }
+
+    int stage = 0, cur_b = -1;
+    uint32_t parity = 0;
+    for (int i = 0; i < nrows; ++i) {
+        if (cc.b != cur_b) {   // block-uniform: (re)load the utterance's class ids
+            cur_b = cc.b;
+            const int Ub = Ub_arr[cur_b];
+            const int64_t toff = toff_arr[cur_b];
+            for (int k = tid; k < Lp; k += kStreamThreads) {
+                int cls;
+                if (k == 0) cls = blank;
+                else if (k == 1) cls = -2;       // slot of lse2
+                else if (k < 4) cls = -3;        // unused header slots -> 0
+                else if (k - 4 < Ub) {
+                    const int64_t idx = toff + (k - 4);
+                    long long c = idx < tnumel ? targets[idx] : -1;
+                    if (c < 0 || c >= V || c == blank) {
+                        atomicOr(&hdr[0], 4);
+                        c = c < 0 ? 0 : (c >= V ? V - 1 : c);
+                    }
+                    cls = (int)c;
+                } else cls = -1;                 // beyond U_b -> -inf
+                cls_s[k] = cls;
+            }
+            __syncthreads();
+        }
+        mbar_wait(bar0 + 8 * stage, parity);
+        const float *grow = logits + ((size_t)cc.b * T + cc.t) * V;
+        const int head = (int)(((uintptr_t)grow & 15) >> 2);
+        const int nch = (head + V + 3) >> 2;
+        const unsigned char *slot = smem + (size_t)stage * slot_bytes;
+        const float4 *s4 = (const float4 *)slot;
+        const float *srow = (const float *)slot + head;
+
+        float4 v[MAXC];
+        float mx = CTC_NEG_INF;
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) {
+            const int c = tid + k * kStreamThreads;
+            float4 x = make_float4(CTC_NEG_INF, CTC_NEG_INF, CTC_NEG_INF, CTC_NEG_INF);
+            if (c < nch) {
+                x = s4[c];
+                if (c == 0 || c == nch - 1) {
+                    const int e = 4 * c - head;
+                    if (e < 0 || e >= V) x.x = CTC_NEG_INF;
+                    if (e + 1 < 0 || e + 1 >= V) x.y = CTC_NEG_INF;
+                    if (e + 2 < 0 || e + 2 >= V) x.z = CTC_NEG_INF;
+                    if (e + 3 < 0 || e + 3 >= V) x.w = CTC_NEG_INF;
+                }
+                mx = fmaxf(mx, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
+            }
+            v[k] = x;
+        }
+        // gather the frame's label logits while the row is still in the slot
+        float xg[3];
+        int cg[3];
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+            const int k = tid + kk * kStreamThreads;
+            cg[kk] = -1; xg[kk] = 0.f;
+            if (k < Lp) { cg[kk] = cls_s[k]; if (cg[kk] >= 0) xg[kk] = srow[cg[kk]]; }
+        }
+        float *rd = red + (i & 1) * 8;
+        mx = warp_max(mx);
+        if (lane == 0) rd[warp] = mx;
+        __syncthreads();                                   // B1: slot fully consumed
+        if (tid == 0 && issued < nrows) {                  // refill it with row i + nst
+            issue_row(logits + ((size_t)pc.b * T + pc.t) * V, V, end16, slot0 + stage * slot_bytes,
+                      bar0 + 8 * stage, 0);
+            cursor_next(pc, Tb_arr, B);
+            ++issued;
+        }
+        const float m = fmaxf(fmaxf(rd[0], rd[1]), fmaxf(rd[2], rd[3]));
+        const float m2 = m * kLog2e;
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) {
+            sum += ex2f(fmaf(v[k].x, kLog2e, -m2)) + ex2f(fmaf(v[k].y, kLog2e, -m2));
+            sum += ex2f(fmaf(v[k].z, kLog2e, -m2)) + ex2f(fmaf(v[k].w, kLog2e, -m2));
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) rd[4 + warp] = sum;
+        __syncthreads();                                   // B2
+        const float lse2 = m2 + lg2f((rd[4] + rd[5]) + (rd[6] + rd[7]));
+        float *frame = lp_lab + ((size_t)cc.b * T + cc.t) * Lp;
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+            const int k = tid + kk * kStreamThreads;
+            if (k < Lp) {
+                float o;
+                if (cg[kk] >= 0) o = fmaf(xg[kk], kLog2e, -lse2);
+                else o = cg[kk] == -2 ? lse2 : (cg[kk] == -3 ? 0.f : CTC_NEG_INF);
+                frame[k] = o;
+            }
+        }
+        cursor_next(cc, Tb_arr, B);
+        if (++stage == nst) { stage = 0; parity ^= 1; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// helpers for k3
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void zero_span(float *p, size_t n, int tid) {   // CTA-wide
+    const size_t head = ((16 - ((uintptr_t)p & 15)) & 15) >> 2;
+    const size_t h = head < n ? head : n;
+    if ((size_t)tid < h) p[tid] = 0.f;
+    float4 *q = (float4 *)(p + h);
+    const size_t n4 = (n - h) >> 2;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t i = tid; i < n4; i += kStreamThreads) q[i] = z;
+    const size_t done = h + (n4 << 2);
+    if (done + tid < n) p[done + tid] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k3: fused gradient.  Phase A: valid frames (re-read logits via TMA, write g*(softmax - occupancy)).
+//     Phase B: padded frames -> zeros.  Each CTA takes an equal share of both.
+// Stage = logits row hull + the frame of `gam` (occupancies + lse2) of the same (b,t).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kStreamThreads)
+k3_grad(const float *__restrict__ logits, const int64_t *__restrict__ targets, int64_t tnumel,
+        const int *__restrict__ Tb_arr, const int *__restrict__ Ub_arr, const int64_t *__restrict__ toff_arr,
+        const int *__restrict__ flags, const int *__restrict__ rowstart, const float *__restrict__ gam,
+        const float *__restrict__ grad_out, int64_t go_stride, int reduction, float inv_batch,
+        float *__restrict__ grad, int B, int T, int V, int Lp, int blank, int zero_inf, int nst,
+        uint32_t slot_bytes, uint32_t stage_bytes) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int R = rowstart[B];
+    {   // ---------------- phase A ----------------
+        const int r0 = (int)((long long)R * blockIdx.x / gridDim.x);
+        const int r1 = (int)((long long)R * (blockIdx.x + 1) / gridDim.x);
+        const int nrows = r1 - r0;
+        uint64_t *bars = (uint64_t *)(smem + (size_t)nst * stage_bytes);
+        int *pcls = (int *)(bars + nst);      // [Lp] class of patch slot k (0 = blank, k>=1: label k-1)
+        int *pnext = pcls + Lp;               // [Lp] next slot with the same class, or -1
+        int *pfirst = pnext + Lp;             // [Lp] 1 if first occurrence of its class
+        const uint32_t slot0 = smem_u32(smem), bar0 = smem_u32(bars);
+        if (nrows > 0) {
+            if (tid == 0) {
+                for (int s = 0; s < nst; ++s) mbar_init(bar0 + 8 * s, 1);
+                fence_mbar_init();
+            }
+            __syncthreads();
+            const uintptr_t end16 = ((uintptr_t)logits + (size_t)B * T * V * 4) & ~(uintptr_t)15;
+            const uint32_t gam_bytes = (uint32_t)Lp * 4;
+            RowCursor pc, cc;
+            cursor_seek(cc, r0, rowstart, Tb_arr, B);
+            pc = cc;
+            int issued = 0;
+            auto issue = [&](int stg) {
+                const uint32_t dst = slot0 + stg * stage_bytes, bar = bar0 + 8 * stg;
+                if (zero_inf && flags[pc.b]) {
+                    mbar_arrive(bar);                      // zeroed utterance: nothing to read
+                } else {
+                    const size_t fr = (size_t)pc.b * T + pc.t;
+                    issue_row(logits + fr * V, V, end16, dst, bar, gam_bytes);
+                    tma_load_1d(dst + slot_bytes, gam + fr * Lp, gam_bytes, bar);
+                }
+                cursor_next(pc, Tb_arr, B);
+                ++issued;
+            };
+            if (tid == 0) while (issued < nst && issued < nrows) issue(issued);
+
+            int stage = 0, cur_b = -1, Ub = 0;
+            uint32_t parity = 0;
+            float g = 0.f;
+            bool zero_rows = false;
+            for (int i = 0; i < nrows; ++i) {
+                if (cc.b != cur_b) {   // block-uniform: per-utterance scale and patch tables
+                    cur_b = cc.b;
+                    Ub = Ub_arr[cur_b];
+                    const int infeasible = flags[cur_b];
+                    const float go = grad_out[go_stride ? (int64_t)cur_b * go_stride : 0];
+                    g = go * (reduction == 1 ? inv_batch / (float)(Ub > 1 ? Ub : 1) : 1.f);
+                    zero_rows = infeasible && zero_inf;
+                    if (infeasible && !zero_inf) g = __int_as_float(0x7fc00000);   // torch: NaN frames
+                    const int64_t toff = toff_arr[cur_b];
+                    __syncthreads();   // previous utterance's patch reads are done
+                    for (int k = tid; k <= Ub; k += kStreamThreads) {
+                        long long c = blank;
+                        if (k > 0) {
+                            const int64_t idx = toff + (k - 1);
+                            c = idx < tnumel ? targets[idx] : 0;
+                            c = c < 0 ? 0 : (c >= V ? V - 1 : c);
+                        }
+                        pcls[k] = (int)c;
+                    }
+                    __syncthreads();
+                    for (int k = tid; k <= Ub; k += kStreamThreads) {
+                        const int c = pcls[k];
+                        int first = 1, nxt = -1;
+                        for (int j = 0; j < k; ++j) if (pcls[j] == c) { first = 0; break; }
+                        for (int j = k + 1; j <= Ub; ++j) if (pcls[j] == c) { nxt = j; break; }
+                        pfirst[k] = first; pnext[k] = nxt;
+                    }
+                    __syncthreads();
+                }
+                mbar_wait(bar0 + 8 * stage, parity);
+                float *grow = grad + ((size_t)cc.b * T + cc.t) * V;
+                if (zero_rows) {
+                    zero_span(grow, (size_t)V, tid);
+                    __syncthreads();
+                    if (tid == 0 && issued < nrows) issue(stage);
+                } else {
+                    const int head = (int)(((uintptr_t)grow & 15) >> 2);
+                    const int nch = (head + V + 3) >> 2;
+                    const unsigned char *slot = smem + (size_t)stage * stage_bytes;
+                    const float4 *s4 = (const float4 *)slot;
+                    const float *srow = (const float *)slot + head;
+                    const float *gf = (const float *)(slot + slot_bytes);
+                    const float lse2 = gf[1];
+                    float4 *g4 = (float4 *)((uintptr_t)grow & ~(uintptr_t)15);
+#pragma unroll 3
+                    for (int c = tid; c < nch; c += kStreamThreads) {
+                        const float4 x = s4[c];
+                        float4 y;
+                        y.x = g * ex2f(fmaf(x.x, kLog2e, -lse2));
+                        y.y = g * ex2f(fmaf(x.y, kLog2e, -lse2));
+                        y.z = g * ex2f(fmaf(x.z, kLog2e, -lse2));
+                        y.w = g * ex2f(fmaf(x.w, kLog2e, -lse2));
+                        const int e = 4 * c - head;
+                        if (e >= 0 && e + 3 < V) {
+                            g4[c] = y;
+                        } else {
+                            if (e >= 0 && e < V) grow[e] = y.x;
+                            if (e + 1 >= 0 && e + 1 < V) grow[e + 1] = y.y;
+                            if (e + 2 >= 0 && e + 2 < V) grow[e + 2] = y.z;
+                            if (e + 3 >= 0 && e + 3 < V) grow[e + 3] = y.w;
+                        }
+                    }
+                    // sparse occupancy correction for blank + first occurrence of each label
+                    float pv[2];
+                    int pc_[2];
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const int k = tid + kk * kStreamThreads;
+                        pc_[kk] = -1; pv[kk] = 0.f;
+                        if (k <= Ub && pfirst[k]) {
+                            float occ = 0.f;
+                            for (int j = k; j >= 0; j = pnext[j]) occ += (j == 0 ? gf[0] : gf[3 + j]);
+                            const int c = pcls[k];
+                            pc_[kk] = c;
+                            pv[kk] = g * (ex2f(fmaf(srow[c], kLog2e, -lse2)) - occ);
+                        }
+                    }
+                    __syncthreads();                       // dense stores ordered before the patch; slot free
+                    if (tid == 0 && issued < nrows) issue(stage);
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) if (pc_[kk] >= 0) grow[pc_[kk]] = pv[kk];
+                }
+                cursor_next(cc, Tb_arr, B);
+                if (++stage == nst) { stage = 0; parity ^= 1; }
+            }
+        }
+    }
+    {   // ---------------- phase B: padded frames ----------------
+        const long long Z = (long long)B * T - R;
+        if (Z <= 0) return;
+        long long z = Z * blockIdx.x / gridDim.x;
+        const long long z1 = Z * (blockIdx.x + 1) / gridDim.x;
+        if (z >= z1) return;
+        int lo = 0, hi = B - 1;   // smallest b with pad-prefix(b+1) > z ; pad-prefix(b) = b*T - rowstart[b]
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((long long)(mid + 1) * T - rowstart[mid + 1] > z) hi = mid; else lo = mid + 1;
+        }
+        int b = lo;
+        int t = Tb_arr[b] + (int)(z - ((long long)b * T - rowstart[b]));
+        while (z < z1) {
+            const long long run = (z1 - z) < (long long)(T - t) ? (z1 - z) : (long long)(T - t);
+            zero_span(grad + ((size_t)b * T + t) * V, (size_t)run * V, tid);
+            z += run;
+            ++b;
+            while (b < B && Tb_arr[b] >= T) ++b;
+            if (b >= B) break;
+            t = Tb_arr[b];
+        }
+    }
+}
+
+}  // namespace ctcb200

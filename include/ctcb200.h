@@ -1,0 +1,119 @@
+/* ctcb200 -- B200-native (sm_100a) CTC loss + gradient w.r.t. logits.  C ABI.
+ *
+ * Drop-in boundary for the CTC branch of the joint CTC/attention objective of
+ * zqs01/ASR_chinese_e2e.  The reference is pure Python and has no FFI and no CTC
+ * call site; each entry point below cites the reference interface
+ * whose tensors it consumes / the torch op it replaces:
+ *
+ *   logits   f32 [B,T,V] batch-major, contiguous   <- Predictor/Utils/loss.py:10 ("pred: N x T x C"),
+ *                                                     encoder tap Predictor/Models/transformer_official.py:76
+ *   targets  i64 [B,Umax] padded with 0 (or 1-D)   <- data/data_loader/ai_shell_1.py:75-88 (tgt_for_input),
+ *                                                     Predictor/data_handler/padder.py:6-27
+ *   in_len / tgt_len  i64 [B]                      <- ai_shell_1.py:80-84 (wave_len, tgt_len)
+ *   blank = 0 = PAD                                <- Predictor/data_handler/vocab.py:10,17
+ *   loss consumer                                  <- Predictor/Models/transformer_official.py:83-104
+ *                                                     (cal_metrics / iterate: loss.backward()),
+ *                                                     Trainer/trainer11.py:57,73-74
+ *
+ * Semantics (the op BASELINE.json names):
+ *   F.ctc_loss(F.log_softmax(logits,-1).transpose(0,1), targets, in_len, tgt_len,
+ *              blank, reduction, zero_infinity)  and its gradient w.r.t. logits.
+ *
+ * Rules of the boundary
+ *   - plain C types only; every pointer except host out-params is a DEVICE pointer;
+ *   - the caller owns every buffer including the workspace; the library allocates
+ *     nothing on the device and retains no pointer after return;
+ *   - all work is enqueued asynchronously on `stream`; no internal synchronisation;
+ *   - return 0 on success, a negative ctcb200_error on bad arguments, a positive
+ *     cudaError_t if a launch failed.  No exceptions, no exit(), no CPU fallback;
+ *   - data-dependent conditions are not errors: an infeasible utterance yields
+ *     nll=+inf (0 with zero_infinity) exactly like torch.  Invalid lengths / labels
+ *     are clamped for memory safety and reported in a device status word
+ *     (ctcb200_read_status, debug use: it synchronises the stream);
+ *   - deterministic: no floating-point atomics; repeated calls are bit-identical.
+ *
+ * Limits: V >= 2, 1 <= T, 0 <= Umax <= 255, V*4 bytes must fit a shared-memory
+ * stage (V <= 16384); logits / grad_logits base addresses 16-byte aligned.
+ */
+#ifndef CTCB200_H_
+#define CTCB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTCB200_VERSION 100 /* 0.1.0 */
+
+typedef void *ctcb200_stream_t; /* cudaStream_t */
+
+enum ctcb200_error {
+    CTCB200_OK = 0,
+    CTCB200_ERR_NULL = -1,      /* a required pointer is NULL */
+    CTCB200_ERR_SHAPE = -2,     /* B<0, T<1, V<2 or V too large for a shared-memory stage */
+    CTCB200_ERR_BLANK = -3,     /* blank not in [0,V) */
+    CTCB200_ERR_UMAX = -4,      /* Umax<0 or Umax>255 */
+    CTCB200_ERR_ALIGN = -5,     /* logits/grad base not 16-byte aligned, workspace not 256-byte aligned */
+    CTCB200_ERR_REDUCTION = -6, /* unknown reduction code */
+    CTCB200_ERR_WORKSPACE = -7, /* workspace_bytes smaller than ctcb200_workspace_bytes() */
+    CTCB200_ERR_NO_DEVICE = -8  /* no CUDA device / not an sm_100 device */
+};
+
+enum ctcb200_reduction { CTCB200_REDUCE_NONE = 0, CTCB200_REDUCE_MEAN = 1, CTCB200_REDUCE_SUM = 2 };
+
+/* bits of the device status word */
+enum ctcb200_status_bits {
+    CTCB200_ST_BAD_INPUT_LENGTH = 1,  /* in_len[b] outside [0,T]: clamped */
+    CTCB200_ST_BAD_TARGET_LENGTH = 2, /* tgt_len[b] outside [0,Umax]: clamped */
+    CTCB200_ST_BAD_LABEL = 4          /* label outside [0,V) or equal to blank */
+};
+
+int ctcb200_version(void);
+const char *ctcb200_strerror(int code);
+
+/* Host-only arithmetic (no CUDA call): bytes of workspace the calls below need. */
+int ctcb200_workspace_bytes(int B, int T, int V, int Umax, size_t *out_bytes);
+
+/* Forward for training (replaces F.log_softmax + aten::_ctc_loss):
+ *   prep + fused log-softmax/label-gather sweep + alpha/beta lattice recursion.
+ * Writes nll[B] (per-utterance negative log-likelihood, zero_infinity applied) and, if
+ * loss_sums != NULL, loss_sums[3] = { sum_b nll_b / max(U_b,1), sum_b nll_b, B }
+ * (the 2-element normaliser pair a data-parallel all-reduce combines).
+ * Leaves the state occupancies in `workspace` for ctcb200_backward.
+ * targets_stride: row stride of the [B,Umax] target matrix, or 0 for 1-D concatenated
+ * targets (then targets_numel bounds the reads). */
+int ctcb200_forward(const float *logits, const int64_t *targets, int64_t targets_stride,
+                    int64_t targets_numel, const int64_t *in_len, const int64_t *tgt_len,
+                    int B, int T, int V, int Umax, int blank, int zero_infinity,
+                    float *nll, float *loss_sums, void *workspace, size_t workspace_bytes,
+                    ctcb200_stream_t stream);
+
+/* Evaluation fast path (forward only, Trainer11.evaluate, trainer11.py:114-129): one sweep of
+ * the logits; no occupancies are kept. Same outputs as ctcb200_forward. */
+int ctcb200_loss_only(const float *logits, const int64_t *targets, int64_t targets_stride,
+                      int64_t targets_numel, const int64_t *in_len, const int64_t *tgt_len,
+                      int B, int T, int V, int Umax, int blank, int zero_infinity,
+                      float *nll, float *loss_sums, void *workspace, size_t workspace_bytes,
+                      ctcb200_stream_t stream);
+
+/* Backward (replaces aten::_ctc_loss_backward + _log_softmax_backward_data):
+ *   grad_logits[b,t,v] = g_b * (softmax(logits)[b,t,v] - occupancy[b,t,v]),  0 for t >= in_len[b].
+ * g_b = grad_out[b*grad_out_stride] * (reduction==MEAN ? inv_batch / max(U_b,1) : 1);
+ * grad_out_stride is 0 for a scalar upstream gradient ('mean'/'sum') and 1 for 'none'.
+ * inv_batch = 1 / (global batch size): pass 1/(world_size*B) when the batch is sharded.
+ * `workspace` must be the one ctcb200_forward filled for the same inputs. */
+int ctcb200_backward(const float *logits, const int64_t *targets, int64_t targets_stride,
+                     int64_t targets_numel, const float *grad_out, int64_t grad_out_stride,
+                     int reduction, float inv_batch, int B, int T, int V, int Umax, int blank,
+                     int zero_infinity, float *grad_logits, const void *workspace,
+                     size_t workspace_bytes, ctcb200_stream_t stream);
+
+/* Debug: copies the device status word to *host_status (synchronises `stream`). */
+int ctcb200_read_status(const void *workspace, int *host_status, ctcb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTCB200_H_ */

@@ -1,0 +1,200 @@
+"""GPU parity: the sm_100a CUDA path (through the C-ABI library) against the CPU oracle.
+
+Tolerances are BASELINE.json's: per-utterance fp32 loss within 1e-5 relative, gradient w.r.t. the
+logits within 1e-4 absolute ('mean' reduction), infeasible utterances compared by class.
+The oracle is torch's CPU ctc_loss (oracle.torch_ref) and, as the adjudicator, the float64
+restatement (oracle.c_oracle).  /root/reference is never read here.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle.c_oracle import ctc_c_f64
+from oracle.synth import make_case, make_config
+from oracle.torch_ref import ref_ctc
+
+pytestmark = pytest.mark.gpu
+
+REL_LOSS = 1e-5
+ABS_GRAD = 1e-4
+
+
+def _op():
+    from asr_chinese_e2e_b200 import ctc_loss_b200
+    return ctc_loss_b200
+
+
+def run_gpu(c, reduction="mean", zero_infinity=False, grad=True, grad_output=None):
+    x = c["logits"].cuda().requires_grad_(grad)
+    loss = _op()(x, c["targets"].cuda(), c["input_lengths"].cuda(), c["target_lengths"].cuda(),
+                 blank=0, reduction=reduction, zero_infinity=zero_infinity)
+    g = None
+    if grad:
+        go = torch.ones_like(loss) if grad_output is None else grad_output.to(loss)
+        loss.backward(go)
+        g = x.grad.detach().cpu()
+    torch.cuda.synchronize()
+    return loss.detach().cpu(), g
+
+
+def assert_loss_close(got, want, what=""):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert np.array_equal(np.isinf(got), np.isinf(want)), f"{what}: inf pattern differs"
+    assert not np.isnan(got).any(), f"{what}: NaN loss"
+    fin = np.isfinite(want)
+    err = np.abs(got[fin] - want[fin]) / np.maximum(np.abs(want[fin]), 1.0)
+    assert err.size == 0 or err.max() <= REL_LOSS, f"{what}: loss rel err {err.max():.3e}"
+
+
+def assert_grad_close(got, want, what="", tol=ABS_GRAD):
+    got, want = got.numpy(), want.numpy() if torch.is_tensor(want) else want
+    assert np.array_equal(np.isnan(got), np.isnan(want)), f"{what}: NaN pattern differs"
+    ok = ~np.isnan(want)
+    err = np.abs(got[ok] - want[ok]).max() if ok.any() else 0.0
+    assert err <= tol, f"{what}: grad abs err {err:.3e}"
+
+
+def check_case(c, zero_infinity=False, what=""):
+    ref_nll, _ = ref_ctc(c["logits"], c["targets"], c["input_lengths"], c["target_lengths"],
+                         reduction="none", zero_infinity=zero_infinity, want_grad=False)
+    nll, _ = run_gpu(c, "none", zero_infinity, grad=False)
+    assert_loss_close(nll, ref_nll, what + " nll(loss_only)")
+    for red in ("mean", "sum"):
+        rl, rg = ref_ctc(c["logits"], c["targets"], c["input_lengths"], c["target_lengths"],
+                         reduction=red, zero_infinity=zero_infinity)
+        gl, gg = run_gpu(c, red, zero_infinity)
+        assert_loss_close(gl, rl, f"{what} {red}")
+        # 'sum' gradients are B*U times larger than 'mean'; the 1e-4 bar is stated on 'mean'
+        assert_grad_close(gg, rg, f"{what} {red}", tol=ABS_GRAD if red == "mean" else 5e-3)
+    # forward-with-grad path must give the same nll as the loss-only path
+    x = c["logits"].cuda().requires_grad_(True)
+    nll2 = _op()(x, c["targets"].cuda(), c["input_lengths"].cuda(), c["target_lengths"].cuda(),
+                 reduction="none", zero_infinity=zero_infinity).detach().cpu()
+    assert_loss_close(nll2, ref_nll, what + " nll(forward)")
+
+
+@pytest.mark.parametrize("zi", [False, True])
+def test_golden_vectors(golden, zi):
+    z, names = golden
+    for name in names:
+        c = {k: torch.from_numpy(z[f"{name}/{k}"]) for k in ("logits", "targets", "input_lengths", "target_lengths")}
+        nll, _ = run_gpu(c, "none", zi, grad=False)
+        assert_loss_close(nll, z[f"{name}/zi{int(zi)}/nll"], name)
+        for red in ("mean", "sum"):
+            gl, gg = run_gpu(c, red, zi)
+            assert_loss_close(gl, z[f"{name}/zi{int(zi)}/{red}/loss"], f"{name} {red}")
+            assert_grad_close(gg, torch.from_numpy(z[f"{name}/zi{int(zi)}/{red}/grad"]), f"{name} {red}",
+                              tol=ABS_GRAD if red == "mean" else 1e-3)
+
+
+@pytest.mark.parametrize("dist", ["D1", "D2"])
+@pytest.mark.parametrize("zi", [False, True])
+def test_small_random(dist, zi):
+    c = make_case(7, 61, 53, 13, 21, dist=dist, n_infeasible=1, n_partial=1)
+    c["target_lengths"][6] = 0                      # empty target
+    check_case(c, zi, f"small {dist}")
+
+
+def test_vocab_alignment_classes():
+    # V*4 mod 16 in {0,4,8,12}: every misalignment of the row hull, incl. the tensor-end tail path
+    for V in (32, 33, 34, 35, 4234 // 8 + 1):
+        c = make_case(3, 17, V, 5, 100 + V)
+        check_case(c, False, f"V={V}")
+
+
+def test_c1_config():
+    c = make_config("C1")                           # B=16, T=200, V=4234, U<=30
+    check_case(c, False, "C1")
+    c = make_config("C1", dist="D2")
+    check_case(c, False, "C1/D2")
+
+
+def test_wide_lattices():
+    # NS=8 (U<=127) and NS=16 (U<=255) variants of the lattice kernel
+    for umax, T, seed in ((100, 260, 31), (200, 450, 32)):
+        c = make_case(3, T, 301, umax, seed, dist="D2", n_partial=1)
+        check_case(c, True, f"Umax={umax}")
+
+
+def test_c4_like_long_with_infeasible():
+    c = make_case(8, 1500, 257, 120, 1004, dist="D1", n_infeasible=2, n_partial=2)
+    check_case(c, True, "C4-like")
+    nll, g = run_gpu(c, "mean", True)
+    il = c["input_lengths"]
+    bad = [1, 2]
+    for b in bad:
+        assert torch.all(g[b] == 0)
+
+
+def test_reduction_none_with_upstream_gradient():
+    c = make_case(5, 40, 29, 8, 77)
+    go = torch.tensor([0.5, -1.0, 2.0, 0.0, 1.5])
+    rl, rg = ref_ctc(c["logits"], c["targets"], c["input_lengths"], c["target_lengths"],
+                     reduction="none", grad_output=go)
+    gl, gg = run_gpu(c, "none", grad_output=go)
+    assert_loss_close(gl, rl, "none")
+    assert_grad_close(gg, rg, "none", tol=1e-3)
+
+
+def test_target_encodings_and_length_dtypes():
+    c = make_case(5, 30, 21, 6, 3)
+    tl = c["target_lengths"]
+    cat = torch.cat([c["targets"][b, : tl[b]] for b in range(5)])
+    op = _op()
+    x = c["logits"].cuda()
+    a = op(x, c["targets"].cuda(), c["input_lengths"].cuda(), tl.cuda(), reduction="none")
+    b1 = op(x, cat.cuda(), c["input_lengths"].cuda(), tl.cuda(), reduction="none")
+    b2 = op(x, cat, c["input_lengths"].int(), tl.int(), reduction="none")          # CPU int32 lengths
+    b3 = op(x, cat.cuda(), tuple(c["input_lengths"].tolist()), tuple(tl.tolist()), reduction="none")
+    assert torch.equal(a, b1) and torch.equal(a, b2) and torch.equal(a, b3)
+
+
+def test_properties_and_determinism_c2_shape():
+    # full BASELINE size: size-independent properties instead of an element-wise oracle
+    c = make_config("C2")
+    B, T, V = c["logits"].shape
+    x = c["logits"].cuda().requires_grad_(True)
+    tg, il, tl = c["targets"].cuda(), c["input_lengths"].cuda(), c["target_lengths"].cuda()
+    op = _op()
+    loss = op(x, tg, il, tl, reduction="mean")
+    loss.backward()
+    g1 = x.grad.clone()
+    nll = op(x.detach(), tg, il, tl, reduction="none")
+    # (1) 'mean' == mean_b(nll_b / max(U_b,1))
+    want = (nll.double() / tl.clamp(min=1).double()).mean()
+    assert abs(loss.item() - want.item()) <= 1e-6 * abs(want.item())
+    # (2) padded frames exactly zero; valid frames sum to ~0 over the vocabulary
+    tmask = torch.arange(T, device="cuda")[None, :] < il[:, None]
+    assert torch.all(g1[~tmask] == 0)
+    rs = g1.sum(-1)[tmask].abs().max().item()
+    assert rs < 1e-7, rs
+    # (3) bit-identical on repeat (no float atomics)
+    x.grad = None
+    op(x, tg, il, tl, reduction="mean").backward()
+    assert torch.equal(g1, x.grad)
+    # (4) sharding: running two halves with the global normaliser reproduces the slab bit-for-bit
+    h = B // 2
+    for sl in (slice(0, h), slice(h, B)):
+        xs = c["logits"][sl].cuda().requires_grad_(True)
+        ls = op(xs, tg[sl], il[sl], tl[sl], reduction="mean", inv_batch=1.0 / B)
+        ls.backward()
+        assert torch.equal(xs.grad, g1[sl])
+    # (5) spot-check a few utterances against the float64 oracle
+    idx = [0, 17, 255]
+    sub = {k: v[idx] for k, v in c.items()}
+    _, n64, g64 = ctc_c_f64(*[sub[k].numpy() for k in ("logits", "targets", "input_lengths", "target_lengths")],
+                            reduction="sum")
+    assert np.abs(nll[idx].cpu().numpy() - n64).max() / np.abs(n64).max() < REL_LOSS
+    scale = 1.0 / (B * tl[idx].clamp(min=1).double().cpu().numpy())
+    assert np.abs(g1[idx].cpu().numpy() - g64 * scale[:, None, None]).max() < ABS_GRAD
+
+
+def test_error_codes_and_no_cpu_fallback():
+    from asr_chinese_e2e_b200 import _lib
+    op = _op()
+    with pytest.raises(_lib.CtcB200Error):
+        op(torch.zeros(1, 4, 5), torch.ones(1, 1, dtype=torch.long), [4], [1])      # CPU logits
+    with pytest.raises(_lib.CtcB200Error):
+        op(torch.zeros(1, 4, 5, device="cuda", dtype=torch.float64), torch.ones(1, 1, dtype=torch.long), [4], [1])
+    with pytest.raises(_lib.CtcB200Error):
+        op(torch.zeros(1, 4, 5, device="cuda"), torch.ones(1, 1, dtype=torch.long), [4], [1], blank=7)
