@@ -64,8 +64,18 @@ def check_case(c, zero_infinity=False, what=""):
                          reduction=red, zero_infinity=zero_infinity)
         gl, gg = run_gpu(c, red, zero_infinity)
         assert_loss_close(gl, rl, f"{what} {red}")
-        # 'sum' gradients are B*U times larger than 'mean'; the 1e-4 bar is stated on 'mean'
-        assert_grad_close(gg, rg, f"{what} {red}", tol=ABS_GRAD if red == "mean" else 5e-3)
+        if red == "mean":
+            assert_grad_close(gg, rg, f"{what} {red}", tol=ABS_GRAD)          # the north-star bar
+        else:
+            # un-normalised gradients are B*U times larger and fp32 log-space rounding (|alpha| ~ T ln V)
+            # shows: adjudicate with the float64 oracle -- we must be no worse than 3x torch's own error
+            _, _, g64 = ctc_c_f64(*[c[k].numpy() for k in ("logits", "targets", "input_lengths", "target_lengths")],
+                                  reduction="sum", zero_infinity=zero_infinity)
+            ok = ~np.isnan(g64)
+            assert np.array_equal(np.isnan(gg.numpy()), ~ok), f"{what}: NaN pattern differs"
+            torch_err = np.abs(rg.numpy()[ok] - g64[ok]).max()
+            our_err = np.abs(gg.numpy()[ok] - g64[ok]).max()
+            assert our_err <= max(1e-3, 3 * torch_err), f"{what} sum: ours {our_err:.3e} vs torch {torch_err:.3e}"
     # forward-with-grad path must give the same nll as the loss-only path
     x = c["logits"].cuda().requires_grad_(True)
     nll2 = _op()(x, c["targets"].cuda(), c["input_lengths"].cuda(), c["target_lengths"].cuda(),
