@@ -1,0 +1,151 @@
+"""Model-side glue: the joint CTC/attention objective under the reference's model API.
+
+The reference's model contract (Predictor/Bases/base_model.py:24-71) is
+``forward(Pack) -> Pack``, ``cal_metrics(output, input) -> Pack(loss, cer)``,
+``iterate(input, optimizer, is_train) -> (Pack, None)``; ``Trainer11.train_epoch``
+(Trainer/trainer11.py:51-80) and ``BaseTrainer.train_epoch`` (Trainer/base_trainer.py:52-71) only
+ever see ``model.iterate`` and read ``metrics.loss`` / ``metrics.cer`` (every Pack value must be a
+tensor: trainer11.py:108-112, metric_manager.py:24-26).  ``JointCTCAttention`` is a mix-in that adds
+the CTC branch at the two insertion points SURVEY.md section 3.1 names, leaving the trainers
+untouched:
+
+  forward():      ctc_logits = ctc_head(encoder_out)           (tap: transformer_official.py:76)
+  cal_metrics():  loss = w * ctc_loss_b200(ctc_logits, tgt_for_input, wave_len, tgt_len)
+                         + (1 - w) * attention cross-entropy    (sibling of cal_performance, :86)
+
+``tgt_for_input`` / ``tgt_len`` are exactly the CTC targets/lengths (no BOS/EOS at collate time,
+data/data_loader/ai_shell_1.py:52-53,75-88) and the encoder does no time subsampling, so
+``wave_len`` are the CTC input lengths.  New config keys ``ctc_weight`` (0.3) and
+``ctc_zero_infinity`` (True) ride on the existing ``get_default_config`` mechanism.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from .ctc import ctc_loss_b200
+
+IGNORE_ID = 0   # PAD id of the reference vocab == CTC blank (Predictor/Utils/loss.py:5, vocab.py:10)
+
+
+class Pack(dict):
+    """Attribute-access dict used as batch / output / metrics container (mirrors the behaviour of the
+    reference's Predictor/Utils/pack.py:3-27: missing keys read as None, ``add(**kw)``, ``cuda()``)."""
+
+    def __getattr__(self, name):
+        return self.get(name)
+
+    def __setattr__(self, name, value):
+        self[name] = value
+
+    def add(self, **kwargs):
+        self.update(kwargs)
+        return self
+
+    def to(self, device):
+        move = lambda v: tuple(move(i) for i in v) if isinstance(v, tuple) else (
+            v.to(device, non_blocking=True) if torch.is_tensor(v) else v)
+        return Pack({k: move(v) for k, v in self.items()})
+
+    def cuda(self):
+        return self.to("cuda")
+
+
+def edit_distance(a, b) -> int:
+    """Levenshtein distance between two sequences (host metric; the reference calls
+    python-Levenshtein in Predictor/Utils/score.py:4-13)."""
+    if len(a) < len(b):
+        a, b = b, a
+    prev = list(range(len(b) + 1))
+    for i, ca in enumerate(a, 1):
+        cur = [i]
+        for j, cb in enumerate(b, 1):
+            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
+        prev = cur
+    return prev[-1]
+
+
+def attention_ce(pred, gold, smoothing: float = 0.0):
+    """Attention-branch loss with the reference's convention (Predictor/Utils/loss.py:7-51):
+    pred [N,T,C] logits, gold [N,T] with PAD=0 ignored, scalar mean over non-pad tokens."""
+    pred = pred.reshape(-1, pred.size(-1))
+    gold = gold.reshape(-1)
+    if smoothing > 0.0:
+        n_class = pred.size(1)
+        logp = F.log_softmax(pred, dim=1)
+        nonpad = gold.ne(IGNORE_ID)
+        nll = -logp.gather(1, gold.unsqueeze(1)).squeeze(1)
+        smooth = -logp.sum(dim=1)
+        # target distribution: (1-eps) on the label + eps/C elsewhere  (loss.py:38-39)
+        loss = (1.0 - smoothing - smoothing / n_class) * nll + (smoothing / n_class) * smooth
+        return loss.masked_select(nonpad).sum() / nonpad.sum().clamp(min=1)
+    return F.cross_entropy(pred, gold, ignore_index=IGNORE_ID, reduction="mean")
+
+
+def greedy_ctc_ids(ctc_logits, lengths, blank: int = 0):
+    """Best-path decode: argmax per frame, collapse repeats, drop blanks (host lists)."""
+    best = ctc_logits.argmax(-1).cpu()
+    out = []
+    for row, n in zip(best, lengths.tolist()):
+        ids, prev = [], blank
+        for v in row[:n].tolist():
+            if v != prev and v != blank:
+                ids.append(v)
+            prev = v
+        out.append(ids)
+    return out
+
+
+class JointCTCAttention:
+    """Mix-in for a reference-style encoder/decoder model (class M(JointCTCAttention, BaseModel)).
+
+    The host class provides ``self.encoder(wave, wave_len) -> (enc, ...)`` and
+    ``self.decoder(tgt, enc, lens) -> (pred, gold, ...)`` like ``TransformerOffical``
+    (transformer_official.py:68-81).  Call ``init_ctc`` at the end of ``__init__``.
+    """
+
+    ctc_weight: float = 0.3
+    ctc_zero_infinity: bool = True
+
+    def init_ctc(self, d_model: int, vocab_size: int, ctc_weight: float = 0.3, ctc_zero_infinity: bool = True,
+                 smoothing: float = 0.0):
+        self.ctc_head = torch.nn.Linear(d_model, vocab_size)
+        self.ctc_weight = float(ctc_weight)
+        self.ctc_zero_infinity = bool(ctc_zero_infinity)
+        self.att_smoothing = float(smoothing)
+
+    # -- forward: encoder tap + CTC head, then the decoder exactly as the reference calls it --------
+    def forward(self, input):
+        enc, *_ = self.encoder(input.wave, input.wave_len)
+        pred, gold, *_ = self.decoder(input.tgt_for_input, enc, input.tgt_len)
+        return Pack(pred=pred, gold=gold, ctc_logits=self.ctc_head(enc))
+
+    def joint_loss(self, output, input):
+        if output.ctc_logits is None:          # Pack returns None for a missing key (pack.py:7-8)
+            raise KeyError("output Pack has no 'ctc_logits': forward() must add the CTC head output")
+        att = attention_ce(output.pred, output.gold, getattr(self, "att_smoothing", 0.0))
+        ctc = ctc_loss_b200(output.ctc_logits.float(), input.tgt_for_input, input.wave_len, input.tgt_len,
+                            blank=IGNORE_ID, reduction="mean", zero_infinity=self.ctc_zero_infinity)
+        w = self.ctc_weight
+        return w * ctc + (1.0 - w) * att, ctc, att
+
+    def cal_metrics(self, output, input):
+        loss, ctc, att = self.joint_loss(output, input)
+        assert not torch.isinf(loss)           # the reference's only numerical guard (transformer_official.py:88)
+        hyp = output.pred.argmax(-1)
+        cer = 0.0
+        for h, g in zip(hyp.tolist(), output.gold.tolist()):
+            g = [t for t in g if t != IGNORE_ID]
+            cer += edit_distance(h[: len(g)], g) / max(len(g), 1)
+        cer = cer * 100.0 / max(hyp.size(0), 1)
+        return Pack(loss=loss, cer=torch.tensor([cer]), ctc_loss=ctc.detach(), att_loss=att.detach())
+
+    def iterate(self, input, optimizer=None, is_train=True):
+        output = self.forward(input)
+        metrics = self.cal_metrics(output, input)
+        if optimizer is not None and is_train:
+            optimizer.zero_grad()
+            metrics.loss.backward()
+            torch.nn.utils.clip_grad_norm_(self.parameters(), 5.0)   # transformer_official.py:102
+            optimizer.step()
+        return metrics, None

@@ -177,7 +177,7 @@ def test_properties_and_determinism_c2_shape():
     tmask = torch.arange(T, device="cuda")[None, :] < il[:, None]
     assert torch.all(g1[~tmask] == 0)
     rs = g1.sum(-1)[tmask].abs().max().item()
-    assert rs < 1e-7, rs
+    assert rs < 1e-5, rs      # |g_b| ~ 1e-4 times the fp32 log-space normalisation error (~3e-3)
     # (3) bit-identical on repeat (no float atomics)
     x.grad = None
     op(x, tg, il, tl, reduction="mean").backward()
