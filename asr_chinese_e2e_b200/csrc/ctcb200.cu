@@ -98,7 +98,7 @@ cudaError_t launch_k2(cudaStream_t s, const int64_t *targets, int64_t tnumel, co
     cudaError_t e = cudaFuncSetAttribute(k2_lattice<NS, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::SMEM);
     if (e != cudaSuccess) return e;
-    k2_lattice<NS, GRAD><<<B, 64, C::SMEM, s>>>(targets, tnumel, Tb, Ub, toff, flags, lp_lab, gam, ab, nll,
+    k2_lattice<NS, GRAD><<<(B + 1) / 2, 128, C::SMEM, s>>>(targets, tnumel, Tb, Ub, toff, flags, lp_lab, gam, ab, nll,
                                                 loss_sums, ticket, B, T, zero_inf);
     return cudaGetLastError();
 }
@@ -242,6 +242,22 @@ int ctcb200_backward(const float *logits, const int64_t *targets, int64_t target
                                                    grad_out, grad_out_stride, reduction, inv_batch, grad_logits,
                                                    B, T, V, g.Lp, blank, zero_infinity, c.nst, c.slot_bytes,
                                                    c.stage_bytes);
+    return (int)cudaGetLastError();
+}
+
+int ctcb200_rescale_grad(float *grad_logits, const float *grad_out, int64_t grad_out_stride,
+                         const float *applied_in, float *applied_out, int B, int T, int V,
+                         ctcb200_stream_t stream) {
+    if (!grad_logits || !grad_out || !applied_in || !applied_out) return CTCB200_ERR_NULL;
+    if (B < 0 || T < 1 || V < 2 || grad_out_stride < 0) return CTCB200_ERR_SHAPE;
+    if (B == 0) return CTCB200_OK;
+    DevInfo dev;
+    int rc = device_info(&dev);
+    if (rc) return rc;
+    int per = (2 * dev.sms + B - 1) / B;
+    if (per < 1) per = 1;
+    k4_rescale<<<dim3(per, B), 256, 0, (cudaStream_t)stream>>>(grad_logits, grad_out, grad_out_stride, applied_in,
+                                                                 applied_out, T, V);
     return (int)cudaGetLastError();
 }
 

@@ -27,7 +27,7 @@ static inline bool geom_for(int Umax, Geom *g) {
 }
 
 // Frame layout (floats), log2 units:  [0] blank, [1] lse2 of the frame, [2..3] unused,
-// [4+j] label slot j (j < U_b; -inf beyond).  In `gam` the same slots hold the posterior
+// [4+j] label slot j (j < U_b; the finite log(0) sentinel -1e30 beyond).  In `gam` the same slots hold the posterior
 // state occupancies: [0] sum over all blank states, [4+j] label state of slot j.
 
 constexpr size_t kAlign = 256;

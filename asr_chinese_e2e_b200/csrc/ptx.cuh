@@ -9,6 +9,9 @@ namespace ctcb200 {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 #define CTC_NEG_INF (__int_as_float(0xff800000))
+// log2(0) sentinel of the lattice (finite, so a-b is never inf-inf); real values are > -1e29 by a wide margin
+constexpr float kNeg = -1.0e30f;
+constexpr float kNegTest = -1.0e29f;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -121,7 +121,8 @@ __device__ __forceinline__ uint32_t issue_row(const float *row, int V, uintptr_t
 
 // ------------------------------------------------------------------------------------------------
 // k1: fused log-softmax statistics + label gather.  One read of each valid frame.
-//   lp_lab[b,t,0] = lp2(blank)   lp_lab[b,t,1] = lse2   lp_lab[b,t,4+j] = lp2(label_j)  (log2 units)
+//   lp_lab[b,t,0] = lp2(blank)   lp_lab[b,t,1] = lse2   lp_lab[b,t,4+j] = lp2(label_j)  (log2 units;
+//   slots beyond U_b hold the finite log(0) sentinel kNeg)
 // MAXC = float4 chunks a thread keeps in registers (128 threads x MAXC x 4 floats >= V + 3).
 // ------------------------------------------------------------------------------------------------
 template <int MAXC>
@@ -182,7 +183,7 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
                         c = c < 0 ? 0 : (c >= V ? V - 1 : c);
                     }
                     cls = (int)c;
-                } else cls = -1;                 // beyond U_b -> -inf
+                } else cls = -1;                 // beyond U_b -> sentinel
                 cls_s[k] = cls;
             }
             __syncthreads();
@@ -251,8 +252,8 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
             const int k = tid + kk * kStreamThreads;
             if (k < Lp) {
                 float o;
-                if (cg[kk] >= 0) o = fmaf(xg[kk], kLog2e, -lse2);
-                else o = cg[kk] == -2 ? lse2 : (cg[kk] == -3 ? 0.f : CTC_NEG_INF);
+                if (cg[kk] >= 0) o = fmaxf(fmaf(xg[kk], kLog2e, -lse2), kNeg);   // -inf logit -> sentinel
+                else o = cg[kk] == -2 ? lse2 : (cg[kk] == -3 ? 0.f : kNeg);
                 frame[k] = o;
             }
         }
@@ -441,6 +442,38 @@ k3_grad(const float *__restrict__ logits, const int64_t *__restrict__ targets, i
             t = Tb_arr[b];
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k4: in-place rescale of a gradient that was produced speculatively with upstream gradient
+// `applied_in[b]` once the real upstream gradient is known.  Exits without touching memory when the
+// two are equal (the usual case: loss.backward() with grad_out == 1), so it costs one launch.
+// grid = (blocks per utterance, B)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k4_rescale(float *__restrict__ grad, const float *__restrict__ go,
+                                                  int64_t go_stride, const float *__restrict__ applied_in,
+                                                  float *__restrict__ applied_out, int T, int V) {
+    const int b = blockIdx.y;
+    const float gnew = go[go_stride ? (int64_t)b * go_stride : 0];
+    const float gold = applied_in[b];
+    if (blockIdx.x == 0 && threadIdx.x == 0) applied_out[b] = gnew;
+    if (gnew == gold) return;
+    const float f = gnew / gold;
+    float *p = grad + (size_t)b * T * V;
+    const size_t n = (size_t)T * V;
+    const size_t head = ((16 - ((uintptr_t)p & 15)) & 15) >> 2;
+    const size_t h = head < n ? head : n;
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+    if (gtid < h) p[gtid] *= f;
+    float4 *q = (float4 *)(p + h);
+    const size_t n4 = (n - h) >> 2;
+    for (size_t i = gtid; i < n4; i += gsz) {
+        float4 v = q[i];
+        v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+        q[i] = v;
+    }
+    const size_t done = h + (n4 << 2);
+    if (done + gtid < n) p[done + gtid] *= f;
 }
 
 }  // namespace ctcb200

@@ -110,6 +110,16 @@ int ctcb200_backward(const float *logits, const int64_t *targets, int64_t target
                      int zero_infinity, float *grad_logits, const void *workspace,
                      size_t workspace_bytes, ctcb200_stream_t stream);
 
+/* Speculative-gradient support.  A caller that wants loss AND gradient from one pass may run
+ * ctcb200_backward right after ctcb200_forward with grad_out == 1 (before autograd has produced the
+ * real upstream gradient) and fix the result up later: this multiplies utterance b's gradient slab
+ * in place by grad_out[b*stride] / applied_in[b] and records grad_out in applied_out[b].  When the
+ * two are equal (loss.backward() with an upstream gradient of 1) the kernel exits without touching
+ * memory, so the usual cost is one empty launch instead of a third sweep. */
+int ctcb200_rescale_grad(float *grad_logits, const float *grad_out, int64_t grad_out_stride,
+                         const float *applied_in, float *applied_out, int B, int T, int V,
+                         ctcb200_stream_t stream);
+
 /* Debug: copies the device status word to *host_status (synchronises `stream`). */
 int ctcb200_read_status(const void *workspace, int *host_status, ctcb200_stream_t stream);
 
