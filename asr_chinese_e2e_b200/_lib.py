@@ -18,7 +18,7 @@ HEADERS = ["ptx.cuh", "layout.h", "stream_kernels.cuh", "lattice_kernel.cuh",
            os.path.join("..", "..", "include", "ctcb200.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "128"]
 
 
 def needs_build() -> bool:
@@ -55,6 +55,7 @@ SIGNATURES = {
     "ctcb200_forward": (_i, _FWD_ARGS),
     "ctcb200_loss_only": (_i, _FWD_ARGS),
     "ctcb200_backward": (_i, [_p, _p, _i64, _i64, _p, _i64, _i, _f, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "ctcb200_rescale_grad": (_i, [_p, _p, _i64, _p, _p, _i, _i, _i, _p]),
     "ctcb200_read_status": (_i, [_p, ctypes.POINTER(_i), _p]),
 }
 

@@ -239,9 +239,17 @@ __device__ __forceinline__ void lattice_dir(unsigned char *smem, int pair, int l
         const int t0 = q * TT;
         const int rows = (Tb - t0) < TT ? (Tb - t0) : TT;
         const uint32_t tile = ring + stg * C::STAGE;
+        if (rows == TT) {                                        // full stage: straight-line, no per-step branch
 #pragma unroll
-        for (int r = 0; r < TT; ++r) {
-            if (r < rows) {
+            for (int r = 0; r < TT; ++r) {
+                const int rr = DIR ? (TT - 1 - r) : r;
+                float lpb, lpl[NL];
+                lat_step<NS, DIR>(L, tile + rr * C::LP_ROW, t0 + rr, lpb, lpl);
+                if (GRAD) stg_vec<NS>(ab_base + (size_t)(t0 + rr) * Sp + NS * lane, L.st);
+            }
+        } else {                                                 // the (single) ragged stage at the end of the utterance
+#pragma unroll 1
+            for (int r = 0; r < rows; ++r) {
                 const int rr = DIR ? (rows - 1 - r) : r;
                 float lpb, lpl[NL];
                 lat_step<NS, DIR>(L, tile + rr * C::LP_ROW, t0 + rr, lpb, lpl);
@@ -278,68 +286,80 @@ __device__ __forceinline__ void lattice_dir(unsigned char *smem, int pair, int l
         const int t0 = q * TT;
         const int rows = (Tb - t0) < TT ? (Tb - t0) : TT;
         const uint32_t tile = ring + stg * C::STAGE;
-        float gbl[TT];                                           // per-lane partial blank occupancy of each row
+        // one phase-2 step: recursion, then gamma = 2^(alpha+beta-lp-ll2); returns this lane's blank part
+        auto step2 = [&](int rr, bool first) -> float {
+            const uint32_t fa = tile + rr * C::LP_ROW;
+            float lpb, lpl[NL];
+            lat_step<NS, DIR>(L, fa, t0 + rr, lpb, lpl);
+            float ot[NS];                                        // the other direction's stored row at t
+            lds_vec<NS>(ot, (GRAD ? tile + TT * C::LP_ROW + rr * C::AB_ROW : bx) + 4 * NS * lane);
+            if (DIR == 0 && first) {                             // midpoint: log-likelihood (warp-uniform branch)
+                float e[NS], m = kNeg * 4.f;
 #pragma unroll
-        for (int r = 0; r < TT; ++r) {
-            gbl[r] = 0.f;
-            if (r < rows && !infeasible && (GRAD || r == 0)) {
-                const int rr = DIR ? (rows - 1 - r) : r;
-                const uint32_t fa = tile + rr * C::LP_ROW;
-                float lpb, lpl[NL];
-                lat_step<NS, DIR>(L, fa, t0 + rr, lpb, lpl);
-                float ot[NS];                                    // the other direction's stored row at t
-                lds_vec<NS>(ot, (GRAD ? tile + TT * C::LP_ROW + rr * C::AB_ROW : bx) + 4 * NS * lane);
-                if (DIR == 0 && n == n1 && r == 0) {             // midpoint: log-likelihood (block-uniform branch)
-                    float e[NS], m = kNeg * 4.f;
-#pragma unroll
-                    for (int j = 0; j < NS; ++j) {
-                        e[j] = (L.st[j] + ot[j]) - ((j & 1) ? lpl[j >> 1] : lpb);
-                        m = fmaxf(m, e[j]);
-                    }
-                    m = warp_max(m);
-                    float s = 0.f;
-#pragma unroll
-                    for (int j = 0; j < NS; ++j) s += ex2f(e[j] - m);
-                    s = warp_sum(s);
-                    ll2 = m + lg2f(s);
-                    infeasible = ll2 < kNegTest;
-                    if (lane == 0) {
-                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch), "f"(ll2) : "memory");
-                        nll[b] = infeasible ? (zero_inf ? 0.f : __int_as_float(0x7f800000)) : -ll2 * kLn2;
-                        flags[b] = infeasible ? 1 : 0;
-                    }
-                    named_bar_sync(bar_id, 64);
+                for (int j = 0; j < NS; ++j) {
+                    e[j] = (L.st[j] + ot[j]) - ((j & 1) ? lpl[j >> 1] : lpb);
+                    m = fmaxf(m, e[j]);
                 }
-                if (GRAD && !infeasible) {
-                    const float cb = lpb + ll2;
-                    float gl[NL];
+                m = warp_max(m);
+                float sm = 0.f;
 #pragma unroll
-                    for (int j = 0; j < NS; ++j) {
-                        const float c = (j & 1) ? (lpl[j >> 1] + ll2) : cb;
-                        const float g = ex2f((L.st[j] + ot[j]) - c);
-                        if (j & 1) gl[j >> 1] = g; else gbl[r] += g;
-                    }
-                    if (NL * lane < Ub) stg_vec<NL>(gam_base + (size_t)(t0 + rr) * Lp + 4 + NL * lane, gl);
+                for (int j = 0; j < NS; ++j) sm += ex2f(e[j] - m);
+                sm = warp_sum(sm);
+                ll2 = m + lg2f(sm);
+                infeasible = ll2 < kNegTest;
+                if (lane == 0) {
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch), "f"(ll2) : "memory");
+                    nll[b] = infeasible ? (zero_inf ? 0.f : __int_as_float(0x7f800000)) : -ll2 * kLn2;
+                    flags[b] = infeasible ? 1 : 0;
                 }
+                named_bar_sync(bar_id, 64);
             }
-        }
-        if (!GRAD || infeasible) break;
-        // deferred cross-lane sums of the blank occupancies: TT independent butterflies, interleaved
+            float gb = 0.f;
+            if (GRAD && !infeasible) {
+                const float cb = lpb + ll2;
+                float gl[NL];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+                for (int j = 0; j < NS; ++j) {
+                    const float c = (j & 1) ? (lpl[j >> 1] + ll2) : cb;
+                    const float g = ex2f((L.st[j] + ot[j]) - c);
+                    if (j & 1) gl[j >> 1] = g; else gb += g;
+                }
+                if (NL * lane < Ub) stg_vec<NL>(gam_base + (size_t)(t0 + rr) * Lp + 4 + NL * lane, gl);
+            }
+            return gb;
+        };
+        const bool first_job = (DIR == 0 && n == n1);
+        if (rows == TT && !first_job) {
+            // full stage: straight-line; the cross-lane sums of the blank occupancies are deferred to
+            // TT independent, interleaved butterflies
+            float gbl[TT];
 #pragma unroll
-            for (int r = 0; r < TT; ++r) gbl[r] += __shfl_xor_sync(0xffffffffu, gbl[r], o);
-        }
-        {
+            for (int r = 0; r < TT; ++r) gbl[r] = step2(DIR ? (TT - 1 - r) : r, false);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int r = 0; r < TT; ++r) gbl[r] += __shfl_xor_sync(0xffffffffu, gbl[r], o);
+            }
             float mine = 0.f;
 #pragma unroll
             for (int r = 0; r < TT; ++r) if (lane == r) mine = gbl[r];
-            if (lane < rows) {                                   // lane r writes the header of row r of the tile
-                const int rr = DIR ? (rows - 1 - lane) : lane;
-                const float lse2v = lds_f32(tile + rr * C::LP_ROW + 4);
-                *(float2 *)(gam_base + (size_t)(t0 + rr) * Lp) = make_float2(mine, lse2v);
+            if (lane < TT) {                                     // lane r writes the header of the r-th processed row
+                const int rr = DIR ? (TT - 1 - lane) : lane;
+                *(float2 *)(gam_base + (size_t)(t0 + rr) * Lp) = make_float2(mine, lds_f32(tile + rr * C::LP_ROW + 4));
+            }
+        } else {
+            // ragged stage, or the stage that holds the midpoint
+#pragma unroll 1
+            for (int r = 0; r < rows; ++r) {
+                const int rr = DIR ? (rows - 1 - r) : r;
+                float gb = step2(rr, first_job && r == 0);
+                if (!GRAD || infeasible) break;
+                gb = warp_sum(gb);
+                if (lane == 0)
+                    *(float2 *)(gam_base + (size_t)(t0 + rr) * Lp) = make_float2(gb, lds_f32(tile + rr * C::LP_ROW + 4));
             }
         }
+        if (!GRAD || infeasible) break;
         __syncwarp();
         if (n_issue < ntot) { if (lane == 0) issue(n_issue); ++n_issue; }
     }

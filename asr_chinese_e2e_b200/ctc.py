@@ -80,66 +80,153 @@ def _check_status(ws, stream):
                                 "(1: input length, 2: target length, 4: label)")
 
 
+# Side streams for the chunk pipeline (torch supplies streams/events; one pair per device).
+_SIDE = {}
+
+
+def _side_streams(dev):
+    key = (dev.type, dev.index)
+    if key not in _SIDE:
+        _SIDE[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+    return _SIDE[key]
+
+
+def _n_chunks(B, requested):
+    n = requested if requested is not None else int(os.environ.get("CTCB200_CHUNKS", "4"))
+    return max(1, min(int(n), B)) if B else 1
+
+
 class _CTCLossB200Fn(torch.autograd.Function):
+    """Forward runs prep + lse/gather sweep + lattice (+ with ``fused``: the gradient sweep, computed
+    speculatively for an upstream gradient of 1).  The batch is cut into utterance chunks that
+    alternate between two side streams, so the latency-bound lattice of one chunk runs under the
+    HBM-bound sweeps of the next; utterances are independent, so chunking changes no result bit."""
+
     @staticmethod
     def forward(ctx, logits, targets, input_lengths, target_lengths, blank, reduction, zero_infinity,
-                inv_batch, max_target_length):
+                inv_batch, max_target_length, fused, chunks):
         x, tg, stride, il, tl, B, T, V, umax = _prepare(logits, targets, input_lengths, target_lengths,
                                                         blank, max_target_length)
         L = _lib.lib()
         need_grad = ctx.needs_input_grad[0]
-        with torch.cuda.device(x.device):
-            stream = torch.cuda.current_stream().cuda_stream
-            ws_bytes = _lib.workspace_bytes(B, T, V, umax)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-            nll = torch.empty(B, dtype=torch.float32, device=x.device)
-            sums = torch.empty(3, dtype=torch.float32, device=x.device)
-            fn = L.ctcb200_forward if need_grad else L.ctcb200_loss_only
-            _lib.check(fn(x.data_ptr(), tg.data_ptr(), stride, tg.numel(), il.data_ptr(), tl.data_ptr(),
-                          B, T, V, umax, int(blank), int(bool(zero_infinity)), nll.data_ptr(),
-                          sums.data_ptr(), ws.data_ptr(), ws_bytes, stream),
-                       "ctcb200_forward" if need_grad else "ctcb200_loss_only")
+        fused = bool(need_grad and fused)
+        red = _RED[reduction]
+        zi = int(bool(zero_infinity))
+        inv_b = float(inv_batch) if inv_batch is not None else (1.0 / max(B, 1))
+        dev = x.device
+        nll = torch.empty(B, dtype=torch.float32, device=dev)
+        grad = torch.empty_like(x) if fused else None
+        n_ch = _n_chunks(B, chunks)
+        per = (B + n_ch - 1) // n_ch if B else 0
+        ws_bytes = _lib.workspace_bytes(max(per, 1), T, V, umax)
+        ws = torch.empty(n_ch * ws_bytes, dtype=torch.uint8, device=dev)
+        one = torch.ones((), dtype=torch.float32, device=dev) if fused else None
+        fwd = L.ctcb200_forward if need_grad else L.ctcb200_loss_only
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream()
+            side = _side_streams(dev) if n_ch > 1 else (main, main)
+            if n_ch > 1:
+                ev0 = torch.cuda.Event()
+                ev0.record(main)
+                side[0].wait_event(ev0)
+                side[1].wait_event(ev0)
+            xs, ts, es = x.element_size() * T * V, 8, 4
+            for c in range(n_ch):
+                lo, hi = c * per, min((c + 1) * per, B)
+                n = hi - lo
+                if n <= 0:
+                    break
+                st = side[c & 1].cuda_stream
+                tgp = tg.data_ptr() + (lo * stride * ts if stride else 0)
+                wsp = ws.data_ptr() + c * ws_bytes
+                # 1-D targets: every chunk sees the whole concatenation and needs its own offset base;
+                # keep it simple and exact by running 1-D targets as a single chunk (see _prepare)
+                _lib.check(fwd(x.data_ptr() + lo * xs, tgp, stride, tg.numel() - lo * stride, il.data_ptr() + lo * 8,
+                               tl.data_ptr() + lo * 8, n, T, V, umax, int(blank), zi, nll.data_ptr() + lo * es,
+                               None, wsp, ws_bytes, st), "ctcb200_forward" if need_grad else "ctcb200_loss_only")
+                if fused:
+                    _lib.check(L.ctcb200_backward(x.data_ptr() + lo * xs, tgp, stride, tg.numel() - lo * stride,
+                                                  one.data_ptr(), 0, red, inv_b, n, T, V, umax, int(blank), zi,
+                                                  grad.data_ptr() + lo * xs, wsp, ws_bytes, st), "ctcb200_backward")
+            if n_ch > 1:
+                for s_ in side:
+                    e_ = torch.cuda.Event()
+                    e_.record(s_)
+                    main.wait_event(e_)
             if _DEBUG:
-                _check_status(ws, stream)
-        if B == 0:
-            nll.zero_(); sums.zero_()
-        ctx.inv_batch = float(inv_batch) if inv_batch is not None else (1.0 / max(B, 1))
-        ctx.cfg = (stride, B, T, V, umax, int(blank), int(bool(zero_infinity)), _RED[reduction], ws_bytes)
+                for c in range(n_ch):
+                    _check_status(ws[c * ws_bytes:], main.cuda_stream)
+        ctx.cfg = (stride, B, T, V, umax, int(blank), zi, red, ws_bytes, per, n_ch, inv_b, fused)
         if need_grad:
-            ctx.save_for_backward(x, tg, ws)
+            if fused:
+                ctx.applied = torch.ones(B, dtype=torch.float32, device=dev)
+                ctx.save_for_backward(grad)
+            else:
+                ctx.save_for_backward(x, tg, ws)
+        if B == 0:
+            return nll if reduction == "none" else nll.sum()
         if reduction == "none":
             return nll
         if reduction == "sum":
-            return sums[1]
-        return sums[0] * ctx.inv_batch
+            return nll.sum()
+        return (nll / tl.clamp(min=1).to(torch.float32)).sum() * inv_b
 
     @staticmethod
     def backward(ctx, grad_out):
-        x, tg, ws = ctx.saved_tensors
-        stride, B, T, V, umax, blank, zi, red, ws_bytes = ctx.cfg
+        stride, B, T, V, umax, blank, zi, red, ws_bytes, per, n_ch, inv_b, fused = ctx.cfg
         go = grad_out.to(dtype=torch.float32).contiguous()
+        L = _lib.lib()
+        if fused:
+            (grad,) = ctx.saved_tensors
+            with torch.cuda.device(grad.device):
+                stream = torch.cuda.current_stream().cuda_stream
+                applied_new = torch.empty_like(ctx.applied)
+                _lib.check(L.ctcb200_rescale_grad(grad.data_ptr(), go.data_ptr(), 1 if red == 0 else 0,
+                                                  ctx.applied.data_ptr(), applied_new.data_ptr(), B, T, V, stream),
+                           "ctcb200_rescale_grad")
+                ctx.applied = applied_new
+            return (grad,) + (None,) * 10
+        x, tg, ws = ctx.saved_tensors
         grad = torch.empty_like(x)
+        xs = x.element_size() * T * V
+        gs = 4 if red == 0 else 0
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream().cuda_stream
-            _lib.check(_lib.lib().ctcb200_backward(
-                x.data_ptr(), tg.data_ptr(), stride, tg.numel(), go.data_ptr(), 1 if red == 0 else 0, red,
-                ctx.inv_batch, B, T, V, umax, blank, zi, grad.data_ptr(), ws.data_ptr(), ws_bytes, stream),
-                "ctcb200_backward")
-        return grad, None, None, None, None, None, None, None, None
+            for c in range(n_ch):
+                lo, hi = c * per, min((c + 1) * per, B)
+                n = hi - lo
+                if n <= 0:
+                    break
+                tgp = tg.data_ptr() + (lo * stride * 8 if stride else 0)
+                _lib.check(L.ctcb200_backward(x.data_ptr() + lo * xs, tgp, stride, tg.numel() - lo * stride,
+                                              go.data_ptr() + lo * gs, 1 if red == 0 else 0, red, inv_b, n, T, V,
+                                              umax, blank, zi, grad.data_ptr() + lo * xs,
+                                              ws.data_ptr() + c * ws_bytes, ws_bytes, stream), "ctcb200_backward")
+        return (grad,) + (None,) * 10
 
 
 def ctc_loss_b200(logits, targets, input_lengths, target_lengths, blank: int = 0,
                   reduction: str = "mean", zero_infinity: bool = False, *, inv_batch=None,
-                  max_target_length=None):
+                  max_target_length=None, fused=None, chunks=None):
     """CTC loss on batch-major logits; same flags and results as ``F.ctc_loss`` (see module doc).
 
     inv_batch: 1/(global batch) for 'mean' when the batch is sharded over ranks (default 1/B).
     max_target_length: upper bound on target_lengths for 1-D targets (avoids one host sync).
+    fused: compute the gradient inside the forward call, speculatively for an upstream gradient of
+        1, and only rescale it in backward if autograd hands over something else (one empty launch
+        otherwise).  This lets the gradient sweep of one chunk overlap the lattice of the next and
+        is the default when the logits require grad (env CTCB200_FUSED=0 to disable); costs one
+        extra [B,T,V] buffer held until backward, like autograd's own saved log-probs would.
+    chunks: utterance chunks of the two-stream pipeline (default env CTCB200_CHUNKS or 4).
     """
     if reduction not in _RED:
         raise ValueError(f"reduction must be one of {list(_RED)}")
+    if fused is None:
+        fused = bool(int(os.environ.get("CTCB200_FUSED", "1")))
+    if torch.is_tensor(targets) and targets.dim() == 1:
+        chunks = 1
     return _CTCLossB200Fn.apply(logits, targets, input_lengths, target_lengths, blank, reduction,
-                                zero_infinity, inv_batch, max_target_length)
+                                zero_infinity, inv_batch, max_target_length, fused, chunks)
 
 
 class CTCLossB200(torch.nn.Module):

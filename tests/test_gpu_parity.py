@@ -199,6 +199,42 @@ def test_properties_and_determinism_c2_shape():
     assert np.abs(g1[idx].cpu().numpy() - g64 * scale[:, None, None]).max() < ABS_GRAD
 
 
+def test_fused_pipeline_equals_unfused_and_rescales():
+    """The chunked two-stream, speculative-gradient path must equal the plain forward/backward path bit for
+    bit, for any chunk count, and apply a non-unit upstream gradient exactly once."""
+    c = make_case(13, 70, 4234 // 4, 17, 555, dist="D2", n_infeasible=1, n_partial=1)
+    op = _op()
+    tg, il, tl = c["targets"].cuda(), c["input_lengths"].cuda(), c["target_lengths"].cuda()
+
+    def run(w=1.0, **kw):
+        x = c["logits"].cuda().requires_grad_(True)
+        loss = op(x, tg, il, tl, reduction="mean", zero_infinity=True, **kw)
+        (loss * w).backward()
+        return loss.detach(), x.grad
+
+    l0, g0 = run(fused=False, chunks=1)
+    for kw in (dict(fused=True, chunks=1), dict(fused=True, chunks=4), dict(fused=False, chunks=3),
+               dict(fused=True, chunks=13)):
+        l1, g1 = run(**kw)
+        assert torch.equal(l0, l1) and torch.equal(g0, g1), kw
+    # ctc_weight-style upstream gradient (JointCTCAttention: loss = 0.3*ctc + 0.7*att)
+    _, gw = run(w=0.3, fused=True, chunks=4)
+    _, gu = run(w=0.3, fused=False, chunks=1)
+    assert torch.allclose(gw, gu, rtol=1e-6, atol=1e-12)
+    # reduction='none' with a per-utterance upstream gradient, and a second backward (retain_graph)
+    x = c["logits"].cuda().requires_grad_(True)
+    nll = op(x, tg, il, tl, reduction="none", zero_infinity=True, fused=True, chunks=2)
+    go = torch.linspace(-1, 2, 13, device="cuda")
+    nll.backward(go, retain_graph=True)
+    ga = x.grad.clone()
+    x.grad = None
+    nll.backward(go)
+    assert torch.equal(ga, x.grad)
+    _, rg = ref_ctc(c["logits"], c["targets"], c["input_lengths"], c["target_lengths"], reduction="none",
+                    zero_infinity=True, grad_output=go.cpu())
+    assert_grad_close(ga.cpu(), rg, "none fused", tol=1e-3)
+
+
 def test_error_codes_and_no_cpu_fallback():
     from asr_chinese_e2e_b200 import _lib
     op = _op()
