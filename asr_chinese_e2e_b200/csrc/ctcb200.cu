@@ -90,6 +90,20 @@ cudaError_t launch_k1(const StreamCfg &c, cudaStream_t s, const float *logits, c
     return cudaGetLastError();
 }
 
+template <int MAXC>
+cudaError_t launch_k3(const StreamCfg &c, cudaStream_t s, const float *logits, const int64_t *targets,
+                      int64_t tnumel, const int *Tb, const int *Ub, const int64_t *toff, const int *flags,
+                      const int *rowstart, const float *gam, const float *grad_out, int64_t go_stride,
+                      int reduction, float inv_batch, float *grad, int B, int T, int V, int Lp, int blank,
+                      int zero_inf) {
+    cudaError_t e = cudaFuncSetAttribute(k3_grad<MAXC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+    if (e != cudaSuccess) return e;
+    k3_grad<MAXC><<<c.grid, kStreamThreads, c.smem, s>>>(logits, targets, tnumel, Tb, Ub, toff, flags, rowstart, gam,
+                                                         grad_out, go_stride, reduction, inv_batch, grad, B, T, V, Lp,
+                                                         blank, zero_inf, c.nst, c.slot_bytes, c.stage_bytes);
+    return cudaGetLastError();
+}
+
 template <int NS, bool GRAD>
 cudaError_t launch_k2(cudaStream_t s, const int64_t *targets, int64_t tnumel, const int *Tb, const int *Ub,
                       const int64_t *toff, int *flags, const float *lp_lab, float *gam, float *ab, float *nll,
@@ -236,13 +250,18 @@ int ctcb200_backward(const float *logits, const int64_t *targets, int64_t target
     const uint32_t gam_stage = (uint32_t)align_up((size_t)g.Lp * 4, 128);
     if ((rc = stream_cfg(V, g.Lp, gam_stage, 3 * (size_t)g.Lp * 4, dev.sms, "CTCB200_K3_NST", "CTCB200_K3_CPS", &c)))
         return rc;
-    cudaError_t e = cudaFuncSetAttribute(k3_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
-    if (e != cudaSuccess) return (int)e;
-    k3_grad<<<c.grid, kStreamThreads, c.smem, s>>>(logits, targets, tnumel, Tb, Ub, toff, flags, rowstart, gam,
-                                                   grad_out, grad_out_stride, reduction, inv_batch, grad_logits,
-                                                   B, T, V, g.Lp, blank, zero_infinity, c.nst, c.slot_bytes,
-                                                   c.stage_bytes);
-    return (int)cudaGetLastError();
+    const int nch_max = (V + 6) >> 2;
+    const int maxc = (nch_max + kStreamThreads - 1) / kStreamThreads;
+    cudaError_t e;
+#define K3_ARGS c, s, logits, targets, tnumel, Tb, Ub, toff, flags, rowstart, gam, grad_out, grad_out_stride, \
+                reduction, inv_batch, grad_logits, B, T, V, g.Lp, blank, zero_infinity
+    if (maxc <= 2) e = launch_k3<2>(K3_ARGS);
+    else if (maxc <= 5) e = launch_k3<5>(K3_ARGS);
+    else if (maxc <= 9) e = launch_k3<9>(K3_ARGS);
+    else if (maxc <= 17) e = launch_k3<17>(K3_ARGS);
+    else e = launch_k3<33>(K3_ARGS);
+#undef K3_ARGS
+    return (int)e;
 }
 
 int ctcb200_rescale_grad(float *grad_logits, const float *grad_out, int64_t grad_out_stride,

@@ -37,7 +37,7 @@ struct LatCfg {
     static constexpr int NL = NS / 2;
     static constexpr int Lp = 4 + 32 * NL;
     static constexpr int Sp = 32 * NS;
-    static constexpr int NSTG = NS >= 16 ? 2 : 4;          // ring depth per warp
+    static constexpr int NSTG = 2;                         // ring depth per warp (16 frames ahead)
     static constexpr uint32_t LP_ROW = Lp * 4;
     static constexpr uint32_t AB_ROW = Sp * 4;
     static constexpr uint32_t STAGE = kLatTT * (LP_ROW + (GRAD ? AB_ROW : 0));

@@ -99,6 +99,15 @@ __device__ __forceinline__ void cursor_next(RowCursor &c, const int *__restrict_
     while (c.t >= c.Tb && c.b + 1 < B) { c.b++; c.t = 0; c.Tb = Tb_arr[c.b]; }
 }
 
+// Balanced split of n items over the grid with 32-bit arithmetic only (a 64-bit division would be a
+// CALL to a software routine and force spills of everything live across it).
+__device__ __forceinline__ void grid_share(int n, int &first, int &count) {
+    const int G = (int)gridDim.x, bid = (int)blockIdx.x;
+    const int base = n / G, rem = n - base * G;
+    first = bid * base + (bid < rem ? bid : rem);
+    count = base + (bid < rem ? 1 : 0);
+}
+
 // Issue the TMA copy of one logits row (its 16-byte hull) into a ring slot.  Called by ONE thread.
 // `end16`: tensor end rounded down to 16; the (at most 3) floats of the very last row that lie past
 // it are fetched with plain loads so that nothing beyond the caller's buffer is ever read.
@@ -134,10 +143,8 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
               int nst, uint32_t slot_bytes) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int R = rowstart[B];
-    const int r0 = (int)((long long)R * blockIdx.x / gridDim.x);
-    const int r1 = (int)((long long)R * (blockIdx.x + 1) / gridDim.x);
-    const int nrows = r1 - r0;
+    int r0, nrows;
+    grid_share(rowstart[B], r0, nrows);
     if (nrows <= 0) return;
 
     uint64_t *bars = (uint64_t *)(smem + (size_t)nst * slot_bytes);
@@ -196,24 +203,28 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
         const float4 *s4 = (const float4 *)slot;
         const float *srow = (const float *)slot + head;
 
+        // interior 16-byte chunks 1..nch-2 lie wholly inside the row: no masking, one compare each;
+        // the two edge chunks (shared with the neighbouring rows) are taken by threads 0 and 1
         float4 v[MAXC];
         float mx = CTC_NEG_INF;
 #pragma unroll
         for (int k = 0; k < MAXC; ++k) {
-            const int c = tid + k * kStreamThreads;
+            const int c = 1 + tid + k * kStreamThreads;
             float4 x = make_float4(CTC_NEG_INF, CTC_NEG_INF, CTC_NEG_INF, CTC_NEG_INF);
-            if (c < nch) {
-                x = s4[c];
-                if (c == 0 || c == nch - 1) {
-                    const int e = 4 * c - head;
-                    if (e < 0 || e >= V) x.x = CTC_NEG_INF;
-                    if (e + 1 < 0 || e + 1 >= V) x.y = CTC_NEG_INF;
-                    if (e + 2 < 0 || e + 2 >= V) x.z = CTC_NEG_INF;
-                    if (e + 3 < 0 || e + 3 >= V) x.w = CTC_NEG_INF;
-                }
-                mx = fmaxf(mx, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
-            }
+            if (c <= nch - 2) x = s4[c];
+            mx = fmaxf(mx, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
             v[k] = x;
+        }
+        float4 ve = make_float4(CTC_NEG_INF, CTC_NEG_INF, CTC_NEG_INF, CTC_NEG_INF);
+        if (tid == 0 || (tid == 1 && nch > 1)) {
+            const int c = tid == 0 ? 0 : nch - 1;
+            ve = s4[c];
+            const int e = 4 * c - head;
+            if (e < 0 || e >= V) ve.x = CTC_NEG_INF;
+            if (e + 1 < 0 || e + 1 >= V) ve.y = CTC_NEG_INF;
+            if (e + 2 < 0 || e + 2 >= V) ve.z = CTC_NEG_INF;
+            if (e + 3 < 0 || e + 3 >= V) ve.w = CTC_NEG_INF;
+            mx = fmaxf(mx, fmaxf(fmaxf(ve.x, ve.y), fmaxf(ve.z, ve.w)));
         }
         // gather the frame's label logits while the row is still in the slot
         float xg[3];
@@ -241,6 +252,10 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
         for (int k = 0; k < MAXC; ++k) {
             sum += ex2f(fmaf(v[k].x, kLog2e, -m2)) + ex2f(fmaf(v[k].y, kLog2e, -m2));
             sum += ex2f(fmaf(v[k].z, kLog2e, -m2)) + ex2f(fmaf(v[k].w, kLog2e, -m2));
+        }
+        if (warp == 0) {
+            sum += ex2f(fmaf(ve.x, kLog2e, -m2)) + ex2f(fmaf(ve.y, kLog2e, -m2));
+            sum += ex2f(fmaf(ve.z, kLog2e, -m2)) + ex2f(fmaf(ve.w, kLog2e, -m2));
         }
         sum = warp_sum(sum);
         if (lane == 0) rd[4 + warp] = sum;
@@ -282,6 +297,7 @@ __device__ __forceinline__ void zero_span(float *p, size_t n, int tid) {   // CT
 //     Phase B: padded frames -> zeros.  Each CTA takes an equal share of both.
 // Stage = logits row hull + the frame of `gam` (occupancies + lse2) of the same (b,t).
 // ------------------------------------------------------------------------------------------------
+template <int MAXC>
 __global__ void __launch_bounds__(kStreamThreads)
 k3_grad(const float *__restrict__ logits, const int64_t *__restrict__ targets, int64_t tnumel,
         const int *__restrict__ Tb_arr, const int *__restrict__ Ub_arr, const int64_t *__restrict__ toff_arr,
@@ -293,9 +309,8 @@ k3_grad(const float *__restrict__ logits, const int64_t *__restrict__ targets, i
     const int tid = threadIdx.x;
     const int R = rowstart[B];
     {   // ---------------- phase A ----------------
-        const int r0 = (int)((long long)R * blockIdx.x / gridDim.x);
-        const int r1 = (int)((long long)R * (blockIdx.x + 1) / gridDim.x);
-        const int nrows = r1 - r0;
+        int r0, nrows;
+        grid_share(R, r0, nrows);
         uint64_t *bars = (uint64_t *)(smem + (size_t)nst * stage_bytes);
         int *pcls = (int *)(bars + nst);      // [Lp] class of patch slot k (0 = blank, k>=1: label k-1)
         int *pnext = pcls + Lp;               // [Lp] next slot with the same class, or -1
@@ -337,7 +352,7 @@ k3_grad(const float *__restrict__ logits, const int64_t *__restrict__ targets, i
                     Ub = Ub_arr[cur_b];
                     const int infeasible = flags[cur_b];
                     const float go = grad_out[go_stride ? (int64_t)cur_b * go_stride : 0];
-                    g = go * (reduction == 1 ? inv_batch / (float)(Ub > 1 ? Ub : 1) : 1.f);
+                    g = go * (reduction == 1 ? inv_batch * __frcp_rn((float)(Ub > 1 ? Ub : 1)) : 1.f);
                     zero_rows = infeasible && zero_inf;
                     if (infeasible && !zero_inf) g = __int_as_float(0x7fc00000);   // torch: NaN frames
                     const int64_t toff = toff_arr[cur_b];
@@ -376,23 +391,28 @@ k3_grad(const float *__restrict__ logits, const int64_t *__restrict__ targets, i
                     const float *gf = (const float *)(slot + slot_bytes);
                     const float lse2 = gf[1];
                     float4 *g4 = (float4 *)((uintptr_t)grow & ~(uintptr_t)15);
-#pragma unroll 3
-                    for (int c = tid; c < nch; c += kStreamThreads) {
-                        const float4 x = s4[c];
-                        float4 y;
-                        y.x = g * ex2f(fmaf(x.x, kLog2e, -lse2));
-                        y.y = g * ex2f(fmaf(x.y, kLog2e, -lse2));
-                        y.z = g * ex2f(fmaf(x.z, kLog2e, -lse2));
-                        y.w = g * ex2f(fmaf(x.w, kLog2e, -lse2));
-                        const int e = 4 * c - head;
-                        if (e >= 0 && e + 3 < V) {
+                    // interior chunks 1..nch-2: aligned float4 in, aligned float4 out, no masking
+#pragma unroll
+                    for (int k = 0; k < MAXC; ++k) {
+                        const int c = 1 + tid + k * kStreamThreads;
+                        if (c <= nch - 2) {
+                            const float4 x = s4[c];
+                            float4 y;
+                            y.x = g * ex2f(fmaf(x.x, kLog2e, -lse2));
+                            y.y = g * ex2f(fmaf(x.y, kLog2e, -lse2));
+                            y.z = g * ex2f(fmaf(x.z, kLog2e, -lse2));
+                            y.w = g * ex2f(fmaf(x.w, kLog2e, -lse2));
                             g4[c] = y;
-                        } else {
-                            if (e >= 0 && e < V) grow[e] = y.x;
-                            if (e + 1 >= 0 && e + 1 < V) grow[e + 1] = y.y;
-                            if (e + 2 >= 0 && e + 2 < V) grow[e + 2] = y.z;
-                            if (e + 3 >= 0 && e + 3 < V) grow[e + 3] = y.w;
                         }
+                    }
+                    if (tid == 0 || (tid == 1 && nch > 1)) {   // the two edge chunks: scalar stores inside the row
+                        const int c = tid == 0 ? 0 : nch - 1;
+                        const float4 x = s4[c];
+                        const int e = 4 * c - head;
+                        if (e >= 0 && e < V) grow[e] = g * ex2f(fmaf(x.x, kLog2e, -lse2));
+                        if (e + 1 >= 0 && e + 1 < V) grow[e + 1] = g * ex2f(fmaf(x.y, kLog2e, -lse2));
+                        if (e + 2 >= 0 && e + 2 < V) grow[e + 2] = g * ex2f(fmaf(x.z, kLog2e, -lse2));
+                        if (e + 3 >= 0 && e + 3 < V) grow[e + 3] = g * ex2f(fmaf(x.w, kLog2e, -lse2));
                     }
                     // sparse occupancy correction for blank + first occurrence of each label
                     float pv[2];
@@ -420,11 +440,13 @@ k3_grad(const float *__restrict__ logits, const int64_t *__restrict__ targets, i
         }
     }
     {   // ---------------- phase B: padded frames ----------------
-        const long long Z = (long long)B * T - R;
-        if (Z <= 0) return;
-        long long z = Z * blockIdx.x / gridDim.x;
-        const long long z1 = Z * (blockIdx.x + 1) / gridDim.x;
-        if (z >= z1) return;
+        const int Zn = B * T - R;
+        if (Zn <= 0) return;
+        int z0, zc;
+        grid_share(Zn, z0, zc);
+        if (zc <= 0) return;
+        long long z = z0;
+        const long long z1 = (long long)z0 + zc;
         int lo = 0, hi = B - 1;   // smallest b with pad-prefix(b+1) > z ; pad-prefix(b) = b*T - rowstart[b]
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;

@@ -15,6 +15,7 @@ provides device memory, the current stream and autograd plumbing only.
 """
 from __future__ import annotations
 
+import math
 import os
 
 import torch
@@ -118,6 +119,10 @@ class _CTCLossB200Fn(torch.autograd.Function):
         grad = torch.empty_like(x) if fused else None
         n_ch = _n_chunks(B, chunks)
         per = (B + n_ch - 1) // n_ch if B else 0
+        # every chunk's slab must start 16-byte aligned: chunk size multiple of 4/gcd(T*V, 4) utterances
+        m = 4 // math.gcd(T * V, 4)
+        per = (per + m - 1) // m * m
+        n_ch = (B + per - 1) // per if B else 1
         ws_bytes = _lib.workspace_bytes(max(per, 1), T, V, umax)
         ws = torch.empty(n_ch * ws_bytes, dtype=torch.uint8, device=dev)
         one = torch.ones((), dtype=torch.float32, device=dev) if fused else None
