@@ -47,13 +47,14 @@ _lib = None
 
 _i, _i64, _sz, _f, _p = ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_float, ctypes.c_void_p
 
-_FWD_ARGS = [_p, _p, _i64, _i64, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]
+_FWD_ARGS = [_p, _p, _i64, _i64, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p, _p]
 SIGNATURES = {
     "ctcb200_version": (_i, []),
     "ctcb200_strerror": (ctypes.c_char_p, [_i]),
     "ctcb200_workspace_bytes": (_i, [_i, _i, _i, _i, ctypes.POINTER(_sz)]),
     "ctcb200_forward": (_i, _FWD_ARGS),
     "ctcb200_loss_only": (_i, _FWD_ARGS),
+    "ctcb200_loss_grad": (_i, [_p, _p, _i64, _i64, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _sz, _p, _p]),
     "ctcb200_backward": (_i, [_p, _p, _i64, _i64, _p, _i64, _i, _f, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "ctcb200_rescale_grad": (_i, [_p, _p, _i64, _p, _p, _i, _i, _i, _p]),
     "ctcb200_read_status": (_i, [_p, ctypes.POINTER(_i), _p]),

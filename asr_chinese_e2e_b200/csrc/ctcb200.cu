@@ -55,53 +55,90 @@ struct StreamCfg {
     size_t smem;
     int grid;
 };
-// ring geometry of the two sweep kernels; extra = bytes appended to every stage / fixed tail
-int stream_cfg(int V, int Lp, uint32_t stage_extra, size_t fixed_extra, int sms, const char *env_nst,
-               const char *env_cps, StreamCfg *c) {
+// Ring geometry of the two sweep kernels.  stage_extra = bytes appended to every stage, fixed_extra =
+// per-CTA tail.  Defaults (env-overridable for experiments) were picked by sweeping on a B200
+// (profiles/): the read-only sweep likes many small CTAs with a shallow ring, the read+write sweep
+// fewer CTAs with a deeper ring; both leave >= 52 KB of shared memory per SM free so that a lattice
+// CTA of another utterance chunk can be co-resident.
+constexpr size_t kLatticeReserve = 52 * 1024;
+int stream_cfg(int V, uint32_t stage_extra, size_t fixed_extra, int sms, int dflt_nst, int dflt_cps,
+               const char *env_nst, const char *env_cps, StreamCfg *c) {
     c->slot_bytes = (uint32_t)align_up((size_t)V * 4 + 32, 128);
     c->stage_bytes = c->slot_bytes + stage_extra;
-    int nst = env_int(env_nst, 3);
+    int nst = env_int(env_nst, dflt_nst);
     if (nst < 2) nst = 2;
     if (nst > 8) nst = 8;
     while (nst > 2 && (size_t)nst * c->stage_bytes + fixed_extra + 8 * nst > kSmemBudget) --nst;
     c->nst = nst;
     c->smem = (size_t)nst * c->stage_bytes + 8 * nst + fixed_extra;
     if (c->smem > kSmemBudget) return CTCB200_ERR_SHAPE;
-    int cps = (int)(kSmemBudget / (c->smem + 1024));   // + per-CTA reserved shared memory
-    if (cps > 4) cps = 4;
+    int cps = (int)((kSmemBudget - kLatticeReserve) / (c->smem + 1024));   // + per-CTA reserved shared memory
+    if (cps > dflt_cps) cps = dflt_cps;
     if (cps < 1) cps = 1;
     cps = env_int(env_cps, cps);
     if (cps < 1) cps = 1;
     c->grid = sms * cps;
-    (void)Lp;
     return 0;
 }
 
-template <int MAXC>
-cudaError_t launch_k1(const StreamCfg &c, cudaStream_t s, const float *logits, const int64_t *targets,
-                      int64_t tnumel, const int *Tb, const int *Ub, const int64_t *toff, const int *rowstart,
-                      float *lp_lab, int *hdr, int B, int T, int V, int Lp, int blank) {
-    cudaError_t e = cudaFuncSetAttribute(k1_lse_gather<MAXC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+struct K1Args {
+    const float *logits; const int64_t *targets; int64_t tnumel; const int *Tb, *Ub; const int64_t *toff;
+    const int *rowstart; float *lp_lab; int *hdr; int B, T, V, Lp, blank;
+    float *grad; int reduction; float inv_batch;   // fused (2-sweep) mode only
+};
+struct K3Args {
+    const float *logits; const int64_t *targets; int64_t tnumel; const int *Tb, *Ub; const int64_t *toff;
+    const int *flags, *rowstart; const float *gam, *grad_out; int64_t go_stride; int reduction; float inv_batch;
+    float *grad; int B, T, V, Lp, blank, zero_inf;
+};
+
+template <int NT, int MAXC, bool EXACT, bool FUSED>
+cudaError_t launch_k1x(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
+    cudaError_t e = cudaFuncSetAttribute(k1_lse_gather<NT, MAXC, EXACT, FUSED>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+    if (e != cudaSuccess) return e;
+    k1_lse_gather<NT, MAXC, EXACT, FUSED><<<c.grid, NT, c.smem, s>>>(
+        a.logits, a.targets, a.tnumel, a.Tb, a.Ub, a.toff, a.rowstart, a.lp_lab, a.hdr, a.B, a.T, a.V, a.Lp,
+        a.blank, c.nst, c.slot_bytes, a.grad, a.reduction, a.inv_batch);
+    return cudaGetLastError();
+}
+template <int NT, int MAXC, bool EXACT>
+cudaError_t launch_k1(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
+    return launch_k1x<NT, MAXC, EXACT, false>(c, s, a);
+}
+template <int NT, int MAXC, bool EXACT>
+cudaError_t launch_k1f(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
+    return launch_k1x<NT, MAXC, EXACT, true>(c, s, a);
+}
+template <int NT, int MAXC, bool EXACT>
+cudaError_t launch_k3(const StreamCfg &c, cudaStream_t s, const K3Args &a) {
+    cudaError_t e = cudaFuncSetAttribute(k3_grad<NT, MAXC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)c.smem);
     if (e != cudaSuccess) return e;
-    k1_lse_gather<MAXC><<<c.grid, kStreamThreads, c.smem, s>>>(logits, targets, tnumel, Tb, Ub, toff, rowstart,
-                                                               lp_lab, hdr, B, T, V, Lp, blank, c.nst,
-                                                               c.slot_bytes);
+    k3_grad<NT, MAXC, EXACT><<<c.grid, NT, c.smem, s>>>(a.logits, a.targets, a.tnumel, a.Tb, a.Ub, a.toff, a.flags,
+                                                        a.rowstart, a.gam, a.grad_out, a.go_stride, a.reduction,
+                                                        a.inv_batch, a.grad, a.B, a.T, a.V, a.Lp, a.blank, a.zero_inf,
+                                                        c.nst, c.slot_bytes, c.stage_bytes);
     return cudaGetLastError();
 }
 
-template <int MAXC>
-cudaError_t launch_k3(const StreamCfg &c, cudaStream_t s, const float *logits, const int64_t *targets,
-                      int64_t tnumel, const int *Tb, const int *Ub, const int64_t *toff, const int *flags,
-                      const int *rowstart, const float *gam, const float *grad_out, int64_t go_stride,
-                      int reduction, float inv_batch, float *grad, int B, int T, int V, int Lp, int blank,
-                      int zero_inf) {
-    cudaError_t e = cudaFuncSetAttribute(k3_grad<MAXC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
-    if (e != cudaSuccess) return e;
-    k3_grad<MAXC><<<c.grid, kStreamThreads, c.smem, s>>>(logits, targets, tnumel, Tb, Ub, toff, flags, rowstart, gam,
-                                                         grad_out, go_stride, reduction, inv_batch, grad, B, T, V, Lp,
-                                                         blank, zero_inf, c.nst, c.slot_bytes, c.stage_bytes);
-    return cudaGetLastError();
+// Instantiation for a vocabulary size: interior 16-byte chunks per row lie between imin and imax
+// depending on the row's misalignment; rounds = ceil(imax / NT); EXACT when every round but the last is
+// full for every row ((rounds-1)*NT <= imin) and `rounds` is one of the compiled sizes.
+#define STREAM_DISPATCH(KERN, NT, rounds, exact, ...)                                                      \
+    ((rounds) <= 2    ? ((exact) && (rounds) == 2 ? KERN<NT, 2, true>(__VA_ARGS__) : KERN<NT, 2, false>(__VA_ARGS__))    \
+     : (rounds) <= 5  ? ((exact) && (rounds) == 5 ? KERN<NT, 5, true>(__VA_ARGS__) : KERN<NT, 5, false>(__VA_ARGS__))    \
+     : (rounds) <= 9  ? ((exact) && (rounds) == 9 ? KERN<NT, 9, true>(__VA_ARGS__) : KERN<NT, 9, false>(__VA_ARGS__))    \
+     : (rounds) <= 17 ? ((exact) && (rounds) == 17 ? KERN<NT, 17, true>(__VA_ARGS__) : KERN<NT, 17, false>(__VA_ARGS__)) \
+                      : ((exact) && (rounds) == 33 ? KERN<NT, 33, true>(__VA_ARGS__) : KERN<NT, 33, false>(__VA_ARGS__)))
+
+static inline void stream_pick(int V, int want_nt, int *nt, int *rounds, bool *exact) {
+    const int imax = ((V + 6) >> 2) - 2, imin = ((V + 3) >> 2) - 2;
+    int n = want_nt == 64 ? 64 : 128;
+    int r = imax <= 0 ? 1 : (imax + n - 1) / n;
+    if (n == 64 && r > 33) { n = 128; r = (imax + n - 1) / n; }   // keep the register-resident row <= 33 chunks
+    *nt = n; *rounds = r;
+    *exact = r >= 2 && (r - 1) * n <= imin;
 }
 
 template <int NS, bool GRAD>
@@ -117,10 +154,21 @@ cudaError_t launch_k2(cudaStream_t s, const int64_t *targets, int64_t tnumel, co
     return cudaGetLastError();
 }
 
-int forward_impl(bool want_grad, const float *logits, const int64_t *targets, int64_t targets_stride,
+struct FusedGrad {          // non-null grad => 2-sweep mode: the sweep writes g*softmax, k3p adds -g*occupancy
+    float *grad; int reduction; float inv_batch;
+};
+
+// Every kernel of the path asks for the maximum shared-memory carveout: a launch whose carveout differs
+// from the previous kernel's makes the SMs drain and reconfigure (several microseconds per launch).
+template <typename K>
+void prefer_max_carveout(K kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const int64_t *targets, int64_t targets_stride,
                  int64_t targets_numel, const int64_t *in_len, const int64_t *tgt_len, int B, int T, int V,
                  int Umax, int blank, int zero_infinity, float *nll, float *loss_sums, void *workspace,
-                 size_t workspace_bytes, ctcb200_stream_t stream) {
+                 size_t workspace_bytes, ctcb200_stream_t stream, ctcb200_event_t sweep_done) {
     Geom g;
     Workspace w;
     int rc = check_common(logits, targets, in_len, tgt_len, B, T, V, Umax, blank, workspace, workspace_bytes,
@@ -140,24 +188,37 @@ int forward_impl(bool want_grad, const float *logits, const int64_t *targets, in
     float *lp_lab = (float *)(ws + w.lp_lab), *gam = (float *)(ws + w.gam), *ab = (float *)(ws + w.ab);
     const int64_t tnumel = targets_stride ? (int64_t)B * targets_stride : targets_numel;
 
+    prefer_max_carveout(k0_prep);
     k0_prep<<<1, 1024, 0, s>>>(in_len, tgt_len, targets_stride, B, T, Umax, hdr, Tb, Ub, flags, toff, rowstart);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
 
     StreamCfg c;
-    if ((rc = stream_cfg(V, g.Lp, 0, 64 + (size_t)g.Lp * 4, dev.sms, "CTCB200_K1_NST", "CTCB200_K1_CPS", &c)))
-        return rc;
-    const int nch_max = (V + 6) >> 2;
-    const int maxc = (nch_max + kStreamThreads - 1) / kStreamThreads;
-#define K1_ARGS c, s, logits, targets, tnumel, Tb, Ub, toff, rowstart, lp_lab, hdr, B, T, V, g.Lp, blank
-    if (maxc <= 2) e = launch_k1<2>(K1_ARGS);
-    else if (maxc <= 5) e = launch_k1<5>(K1_ARGS);
-    else if (maxc <= 9) e = launch_k1<9>(K1_ARGS);
-    else if (maxc <= 17) e = launch_k1<17>(K1_ARGS);
-    else e = launch_k1<33>(K1_ARGS);
-#undef K1_ARGS
+    const bool fused = fg != nullptr;
+    int nt1, rounds1;
+    bool exact1;
+    stream_pick(V, env_int(fused ? "CTCB200_K1F_NT" : "CTCB200_K1_NT", fused ? 128 : 64), &nt1, &rounds1, &exact1);
+    if (fused)
+        rc = stream_cfg(V, 0, 64 + (size_t)g.Lp * 4, dev.sms, 3, 3, "CTCB200_K1F_NST", "CTCB200_K1F_CPS", &c);
+    else
+        rc = stream_cfg(V, 0, 64 + (size_t)g.Lp * 4, dev.sms, nt1 == 64 ? 2 : 3, nt1 == 64 ? 5 : 3,
+                        "CTCB200_K1_NST", "CTCB200_K1_CPS", &c);
+    if (rc) return rc;
+    {
+        const K1Args a = {logits, targets, tnumel, Tb, Ub, toff, rowstart, lp_lab, hdr, B, T, V, g.Lp, blank,
+                          fused ? fg->grad : nullptr, fused ? fg->reduction : 0, fused ? fg->inv_batch : 0.f};
+        if (fused) {
+            if (nt1 == 64) e = STREAM_DISPATCH(launch_k1f, 64, rounds1, exact1, c, s, a);
+            else e = STREAM_DISPATCH(launch_k1f, 128, rounds1, exact1, c, s, a);
+        } else {
+            if (nt1 == 64) e = STREAM_DISPATCH(launch_k1, 64, rounds1, exact1, c, s, a);
+            else e = STREAM_DISPATCH(launch_k1, 128, rounds1, exact1, c, s, a);
+        }
+    }
     if (e != cudaSuccess) return (int)e;
+    if (sweep_done && (e = cudaEventRecord((cudaEvent_t)sweep_done, s)) != cudaSuccess) return (int)e;
 
+    if (env_int("CTCB200_DEBUG_SKIP_LATTICE", 0)) return CTCB200_OK;   // profiling aid: time the sweep alone
     unsigned *ticket = (unsigned *)(hdr + 1);
 #define K2_ARGS s, targets, tnumel, Tb, Ub, toff, flags, lp_lab, gam, ab, nll, loss_sums, ticket, B, T, zero_infinity
     if (want_grad) {
@@ -170,6 +231,16 @@ int forward_impl(bool want_grad, const float *logits, const int64_t *targets, in
         else e = launch_k2<16, false>(K2_ARGS);
     }
 #undef K2_ARGS
+    if (e != cudaSuccess || !fused) return (int)e;
+    {
+        const int per = env_int("CTCB200_K3P_CPS", 32);
+        const size_t smem = 2 * (size_t)g.Lp * 4;
+        prefer_max_carveout(k3p_patch<64>);
+        k3p_patch<64><<<dev.sms * (per < 1 ? 1 : per), 64, smem, s>>>(targets, tnumel, Tb, Ub, toff, flags, rowstart, gam,
+                                                                       fg->grad, fg->reduction, fg->inv_batch, B, T, V,
+                                                                       g.Lp, blank, zero_infinity);
+        e = cudaGetLastError();
+    }
     return (int)e;
 }
 
@@ -208,17 +279,30 @@ int ctcb200_workspace_bytes(int B, int T, int V, int Umax, size_t *out_bytes) {
 int ctcb200_forward(const float *logits, const int64_t *targets, int64_t targets_stride, int64_t targets_numel,
                     const int64_t *in_len, const int64_t *tgt_len, int B, int T, int V, int Umax, int blank,
                     int zero_infinity, float *nll, float *loss_sums, void *workspace, size_t workspace_bytes,
-                    ctcb200_stream_t stream) {
-    return forward_impl(true, logits, targets, targets_stride, targets_numel, in_len, tgt_len, B, T, V, Umax,
-                        blank, zero_infinity, nll, loss_sums, workspace, workspace_bytes, stream);
+                    ctcb200_stream_t stream, ctcb200_event_t sweep_done) {
+    return forward_impl(true, nullptr, logits, targets, targets_stride, targets_numel, in_len, tgt_len, B, T, V, Umax,
+                        blank, zero_infinity, nll, loss_sums, workspace, workspace_bytes, stream, sweep_done);
 }
 
 int ctcb200_loss_only(const float *logits, const int64_t *targets, int64_t targets_stride, int64_t targets_numel,
                       const int64_t *in_len, const int64_t *tgt_len, int B, int T, int V, int Umax, int blank,
                       int zero_infinity, float *nll, float *loss_sums, void *workspace, size_t workspace_bytes,
-                      ctcb200_stream_t stream) {
-    return forward_impl(false, logits, targets, targets_stride, targets_numel, in_len, tgt_len, B, T, V, Umax,
-                        blank, zero_infinity, nll, loss_sums, workspace, workspace_bytes, stream);
+                      ctcb200_stream_t stream, ctcb200_event_t sweep_done) {
+    return forward_impl(false, nullptr, logits, targets, targets_stride, targets_numel, in_len, tgt_len, B, T, V, Umax,
+                        blank, zero_infinity, nll, loss_sums, workspace, workspace_bytes, stream, sweep_done);
+}
+
+int ctcb200_loss_grad(const float *logits, const int64_t *targets, int64_t targets_stride, int64_t targets_numel,
+                      const int64_t *in_len, const int64_t *tgt_len, int B, int T, int V, int Umax, int blank,
+                      int zero_infinity, int reduction, float inv_batch, float *nll, float *loss_sums,
+                      float *grad_logits, void *workspace, size_t workspace_bytes, ctcb200_stream_t stream,
+                      ctcb200_event_t sweep_done) {
+    if (!grad_logits) return CTCB200_ERR_NULL;
+    if ((uintptr_t)grad_logits & 15) return CTCB200_ERR_ALIGN;
+    if (reduction < 0 || reduction > 2) return CTCB200_ERR_REDUCTION;
+    const FusedGrad fg = {grad_logits, reduction, inv_batch};
+    return forward_impl(true, &fg, logits, targets, targets_stride, targets_numel, in_len, tgt_len, B, T, V, Umax,
+                        blank, zero_infinity, nll, loss_sums, workspace, workspace_bytes, stream, sweep_done);
 }
 
 int ctcb200_backward(const float *logits, const int64_t *targets, int64_t targets_stride, int64_t targets_numel,
@@ -248,19 +332,18 @@ int ctcb200_backward(const float *logits, const int64_t *targets, int64_t target
 
     StreamCfg c;
     const uint32_t gam_stage = (uint32_t)align_up((size_t)g.Lp * 4, 128);
-    if ((rc = stream_cfg(V, g.Lp, gam_stage, 3 * (size_t)g.Lp * 4, dev.sms, "CTCB200_K3_NST", "CTCB200_K3_CPS", &c)))
+    if ((rc = stream_cfg(V, gam_stage, 3 * (size_t)g.Lp * 4, dev.sms, 3, 3, "CTCB200_K3_NST", "CTCB200_K3_CPS", &c)))
         return rc;
-    const int nch_max = (V + 6) >> 2;
-    const int maxc = (nch_max + kStreamThreads - 1) / kStreamThreads;
     cudaError_t e;
-#define K3_ARGS c, s, logits, targets, tnumel, Tb, Ub, toff, flags, rowstart, gam, grad_out, grad_out_stride, \
-                reduction, inv_batch, grad_logits, B, T, V, g.Lp, blank, zero_infinity
-    if (maxc <= 2) e = launch_k3<2>(K3_ARGS);
-    else if (maxc <= 5) e = launch_k3<5>(K3_ARGS);
-    else if (maxc <= 9) e = launch_k3<9>(K3_ARGS);
-    else if (maxc <= 17) e = launch_k3<17>(K3_ARGS);
-    else e = launch_k3<33>(K3_ARGS);
-#undef K3_ARGS
+    {
+        const K3Args a = {logits, targets, tnumel, Tb, Ub, toff, flags, rowstart, gam, grad_out, grad_out_stride,
+                          reduction, inv_batch, grad_logits, B, T, V, g.Lp, blank, zero_infinity};
+        int nt, rounds;
+        bool exact;
+        stream_pick(V, env_int("CTCB200_K3_NT", 128), &nt, &rounds, &exact);
+        if (nt == 64) e = STREAM_DISPATCH(launch_k3, 64, rounds, exact, c, s, a);
+        else e = STREAM_DISPATCH(launch_k3, 128, rounds, exact, c, s, a);
+    }
     return (int)e;
 }
 
@@ -275,6 +358,7 @@ int ctcb200_rescale_grad(float *grad_logits, const float *grad_out, int64_t grad
     if (rc) return rc;
     int per = (2 * dev.sms + B - 1) / B;
     if (per < 1) per = 1;
+    prefer_max_carveout(k4_rescale);
     k4_rescale<<<dim3(per, B), 256, 0, (cudaStream_t)stream>>>(grad_logits, grad_out, grad_out_stride, applied_in,
                                                                  applied_out, T, V);
     return (int)cudaGetLastError();

@@ -18,8 +18,9 @@
 
 namespace ctcb200 {
 
-constexpr int kStreamThreads = 128;
-constexpr int kStreamWarps = kStreamThreads / 32;
+// The sweep kernels are templated on NT (threads per CTA = threads per logits row), MAXC (16-byte
+// chunks per thread, ceil((row chunks - 2) / NT)) and EXACT (only the last of the MAXC rounds can run
+// past the row, so the other rounds need no bounds check at all).
 
 // ------------------------------------------------------------------------------------------------
 // k0: one CTA.  Clamp/validate lengths, exclusive scans for rowstart[] and (1-D targets) toff[].
@@ -129,22 +130,76 @@ __device__ __forceinline__ uint32_t issue_row(const float *row, int V, uintptr_t
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-wide fill helpers
+// ------------------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ void zero_span(float *p, size_t n, int tid) {   // CTA-wide
+    const size_t head = ((16 - ((uintptr_t)p & 15)) & 15) >> 2;
+    const size_t h = head < n ? head : n;
+    if ((size_t)tid < h) p[tid] = 0.f;
+    float4 *q = (float4 *)(p + h);
+    const size_t n4 = (n - h) >> 2;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t i = tid; i < n4; i += NT) q[i] = z;
+    const size_t done = h + (n4 << 2);
+    if (done + tid < n) p[done + tid] = 0.f;
+}
+template <int NT>
+__device__ __forceinline__ void fill_span(float *p, size_t n, int tid, float val) {   // CTA-wide, scalar (rare path)
+    for (size_t i = tid; i < n; i += NT) p[i] = val;
+}
+
+// Zero the padded frames (t >= T_b) of the whole batch: every CTA takes an equal share of them.
+template <int NT>
+__device__ __forceinline__ void zero_padded_frames(float *__restrict__ grad, const int *__restrict__ Tb_arr,
+                                                   const int *__restrict__ rowstart, int B, int T, int V, int tid) {
+    const int Zn = B * T - rowstart[B];
+    if (Zn <= 0) return;
+    int z0, zc;
+    grid_share(Zn, z0, zc);
+    if (zc <= 0) return;
+    long long z = z0;
+    const long long z1 = (long long)z0 + zc;
+    int lo = 0, hi = B - 1;   // smallest b with pad-prefix(b+1) > z ; pad-prefix(b) = b*T - rowstart[b]
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((long long)(mid + 1) * T - rowstart[mid + 1] > z) hi = mid; else lo = mid + 1;
+    }
+    int b = lo;
+    int t = Tb_arr[b] + (int)(z - ((long long)b * T - rowstart[b]));
+    while (z < z1) {
+        const long long run = (z1 - z) < (long long)(T - t) ? (z1 - z) : (long long)(T - t);
+        zero_span<NT>(grad + ((size_t)b * T + t) * V, (size_t)run * V, tid);
+        z += run;
+        ++b;
+        while (b < B && Tb_arr[b] >= T) ++b;
+        if (b >= B) break;
+        t = Tb_arr[b];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k1: fused log-softmax statistics + label gather.  One read of each valid frame.
 //   lp_lab[b,t,0] = lp2(blank)   lp_lab[b,t,1] = lse2   lp_lab[b,t,4+j] = lp2(label_j)  (log2 units;
 //   slots beyond U_b hold the finite log(0) sentinel kNeg)
 // MAXC = float4 chunks a thread keeps in registers (128 threads x MAXC x 4 floats >= V + 3).
 // ------------------------------------------------------------------------------------------------
-template <int MAXC>
-__global__ void __launch_bounds__(kStreamThreads)
+// FUSED: the same pass also writes the dense part of the gradient, g_b * softmax(x), straight from the
+// registers that hold the row (2^(x-max) is already there for the sum: one extra FMUL per element),
+// and zeroes the padded frames.  The sparse "- g_b * occupancy" part is added by k3p_patch after the
+// lattice.  This makes loss+grad TWO sweeps of [B,T,V] (read once, write once) instead of three.
+template <int NT, int MAXC, bool EXACT, bool FUSED>
+__global__ void __launch_bounds__(NT)
 k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targets, int64_t tnumel,
               const int *__restrict__ Tb_arr, const int *__restrict__ Ub_arr,
               const int64_t *__restrict__ toff_arr, const int *__restrict__ rowstart,
               float *__restrict__ lp_lab, int *__restrict__ hdr, int B, int T, int V, int Lp, int blank,
-              int nst, uint32_t slot_bytes) {
+              int nst, uint32_t slot_bytes, float *__restrict__ grad, int reduction, float inv_batch) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int r0, nrows;
     grid_share(rowstart[B], r0, nrows);
+    if (FUSED) zero_padded_frames<NT>(grad, Tb_arr, rowstart, B, T, V, tid);
     if (nrows <= 0) return;
 
     uint64_t *bars = (uint64_t *)(smem + (size_t)nst * slot_bytes);
@@ -172,12 +227,14 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
 
     int stage = 0, cur_b = -1;
     uint32_t parity = 0;
+    float g = 0.f;             // FUSED: speculative gradient scale of the current utterance (upstream gradient 1)
     for (int i = 0; i < nrows; ++i) {
         if (cc.b != cur_b) {   // block-uniform: (re)load the utterance's class ids
             cur_b = cc.b;
             const int Ub = Ub_arr[cur_b];
+            if (FUSED) g = reduction == 1 ? inv_batch * __frcp_rn((float)(Ub > 1 ? Ub : 1)) : 1.f;
             const int64_t toff = toff_arr[cur_b];
-            for (int k = tid; k < Lp; k += kStreamThreads) {
+            for (int k = tid; k < Lp; k += NT) {
                 int cls;
                 if (k == 0) cls = blank;
                 else if (k == 1) cls = -2;       // slot of lse2
@@ -209,9 +266,14 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
         float mx = CTC_NEG_INF;
 #pragma unroll
         for (int k = 0; k < MAXC; ++k) {
-            const int c = 1 + tid + k * kStreamThreads;
-            float4 x = make_float4(CTC_NEG_INF, CTC_NEG_INF, CTC_NEG_INF, CTC_NEG_INF);
-            if (c <= nch - 2) x = s4[c];
+            const int c = 1 + tid + k * NT;
+            float4 x;
+            if (EXACT && k < MAXC - 1) {
+                x = s4[c];
+            } else {
+                x = make_float4(CTC_NEG_INF, CTC_NEG_INF, CTC_NEG_INF, CTC_NEG_INF);
+                if (c <= nch - 2) x = s4[c];
+            }
             mx = fmaxf(mx, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
             v[k] = x;
         }
@@ -227,11 +289,12 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
             mx = fmaxf(mx, fmaxf(fmaxf(ve.x, ve.y), fmaxf(ve.z, ve.w)));
         }
         // gather the frame's label logits while the row is still in the slot
-        float xg[3];
-        int cg[3];
+        constexpr int MAXG = (260 + NT - 1) / NT;          // Lp <= 260 frame slots
+        float xg[MAXG];
+        int cg[MAXG];
 #pragma unroll
-        for (int kk = 0; kk < 3; ++kk) {
-            const int k = tid + kk * kStreamThreads;
+        for (int kk = 0; kk < MAXG; ++kk) {
+            const int k = tid + kk * NT;
             cg[kk] = -1; xg[kk] = 0.f;
             if (k < Lp) { cg[kk] = cls_s[k]; if (cg[kk] >= 0) xg[kk] = srow[cg[kk]]; }
         }
@@ -245,31 +308,54 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
             cursor_next(pc, Tb_arr, B);
             ++issued;
         }
-        const float m = fmaxf(fmaxf(rd[0], rd[1]), fmaxf(rd[2], rd[3]));
+        const float m = NT == 128 ? fmaxf(fmaxf(rd[0], rd[1]), fmaxf(rd[2], rd[3])) : fmaxf(rd[0], rd[1]);
         const float m2 = m * kLog2e;
         float sum = 0.f;
 #pragma unroll
         for (int k = 0; k < MAXC; ++k) {
-            sum += ex2f(fmaf(v[k].x, kLog2e, -m2)) + ex2f(fmaf(v[k].y, kLog2e, -m2));
-            sum += ex2f(fmaf(v[k].z, kLog2e, -m2)) + ex2f(fmaf(v[k].w, kLog2e, -m2));
+            v[k].x = ex2f(fmaf(v[k].x, kLog2e, -m2)); v[k].y = ex2f(fmaf(v[k].y, kLog2e, -m2));
+            v[k].z = ex2f(fmaf(v[k].z, kLog2e, -m2)); v[k].w = ex2f(fmaf(v[k].w, kLog2e, -m2));
+            sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
         }
         if (warp == 0) {
-            sum += ex2f(fmaf(ve.x, kLog2e, -m2)) + ex2f(fmaf(ve.y, kLog2e, -m2));
-            sum += ex2f(fmaf(ve.z, kLog2e, -m2)) + ex2f(fmaf(ve.w, kLog2e, -m2));
+            ve.x = ex2f(fmaf(ve.x, kLog2e, -m2)); ve.y = ex2f(fmaf(ve.y, kLog2e, -m2));
+            ve.z = ex2f(fmaf(ve.z, kLog2e, -m2)); ve.w = ex2f(fmaf(ve.w, kLog2e, -m2));
+            sum += (ve.x + ve.y) + (ve.z + ve.w);
         }
         sum = warp_sum(sum);
         if (lane == 0) rd[4 + warp] = sum;
         __syncthreads();                                   // B2
-        const float lse2 = m2 + lg2f((rd[4] + rd[5]) + (rd[6] + rd[7]));
+        const float tot = NT == 128 ? (rd[4] + rd[5]) + (rd[6] + rd[7]) : rd[4] + rd[5];
+        const float lse2 = m2 + lg2f(tot);
         float *frame = lp_lab + ((size_t)cc.b * T + cc.t) * Lp;
 #pragma unroll
-        for (int kk = 0; kk < 3; ++kk) {
-            const int k = tid + kk * kStreamThreads;
+        for (int kk = 0; kk < MAXG; ++kk) {
+            const int k = tid + kk * NT;
             if (k < Lp) {
                 float o;
                 if (cg[kk] >= 0) o = fmaxf(fmaf(xg[kk], kLog2e, -lse2), kNeg);   // -inf logit -> sentinel
                 else o = cg[kk] == -2 ? lse2 : (cg[kk] == -3 ? 0.f : kNeg);
                 frame[k] = o;
+            }
+        }
+        if (FUSED) {
+            // dense gradient: g * softmax = 2^(x-max) * g / sum, from the registers that still hold the row
+            const float sc = g * __frcp_rn(tot);           // softmax = 2^(x-max) / sum: no lse rounding involved
+            float *orow = grad + ((size_t)cc.b * T + cc.t) * V;
+            float4 *g4 = (float4 *)((uintptr_t)orow & ~(uintptr_t)15);
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k) {
+                const int c = 1 + tid + k * NT;
+                if ((EXACT && k < MAXC - 1) || c <= nch - 2)
+                    g4[c] = make_float4(v[k].x * sc, v[k].y * sc, v[k].z * sc, v[k].w * sc);
+            }
+            if (tid == 0 || (tid == 1 && nch > 1)) {       // edge chunks: scalar stores inside the row
+                const int c = tid == 0 ? 0 : nch - 1;
+                const int e = 4 * c - head;
+                if (e >= 0 && e < V) orow[e] = ve.x * sc;
+                if (e + 1 >= 0 && e + 1 < V) orow[e + 1] = ve.y * sc;
+                if (e + 2 >= 0 && e + 2 < V) orow[e + 2] = ve.z * sc;
+                if (e + 3 >= 0 && e + 3 < V) orow[e + 3] = ve.w * sc;
             }
         }
         cursor_next(cc, Tb_arr, B);
@@ -278,27 +364,12 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
 }
 
 // ------------------------------------------------------------------------------------------------
-// helpers for k3
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void zero_span(float *p, size_t n, int tid) {   // CTA-wide
-    const size_t head = ((16 - ((uintptr_t)p & 15)) & 15) >> 2;
-    const size_t h = head < n ? head : n;
-    if ((size_t)tid < h) p[tid] = 0.f;
-    float4 *q = (float4 *)(p + h);
-    const size_t n4 = (n - h) >> 2;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (size_t i = tid; i < n4; i += kStreamThreads) q[i] = z;
-    const size_t done = h + (n4 << 2);
-    if (done + tid < n) p[done + tid] = 0.f;
-}
-
-// ------------------------------------------------------------------------------------------------
 // k3: fused gradient.  Phase A: valid frames (re-read logits via TMA, write g*(softmax - occupancy)).
 //     Phase B: padded frames -> zeros.  Each CTA takes an equal share of both.
 // Stage = logits row hull + the frame of `gam` (occupancies + lse2) of the same (b,t).
 // ------------------------------------------------------------------------------------------------
-template <int MAXC>
-__global__ void __launch_bounds__(kStreamThreads)
+template <int NT, int MAXC, bool EXACT>
+__global__ void __launch_bounds__(NT)
 k3_grad(const float *__restrict__ logits, const int64_t *__restrict__ targets, int64_t tnumel,
         const int *__restrict__ Tb_arr, const int *__restrict__ Ub_arr, const int64_t *__restrict__ toff_arr,
         const int *__restrict__ flags, const int *__restrict__ rowstart, const float *__restrict__ gam,
@@ -357,7 +428,7 @@ k3_grad(const float *__restrict__ logits, const int64_t *__restrict__ targets, i
                     if (infeasible && !zero_inf) g = __int_as_float(0x7fc00000);   // torch: NaN frames
                     const int64_t toff = toff_arr[cur_b];
                     __syncthreads();   // previous utterance's patch reads are done
-                    for (int k = tid; k <= Ub; k += kStreamThreads) {
+                    for (int k = tid; k <= Ub; k += NT) {
                         long long c = blank;
                         if (k > 0) {
                             const int64_t idx = toff + (k - 1);
@@ -367,7 +438,7 @@ k3_grad(const float *__restrict__ logits, const int64_t *__restrict__ targets, i
                         pcls[k] = (int)c;
                     }
                     __syncthreads();
-                    for (int k = tid; k <= Ub; k += kStreamThreads) {
+                    for (int k = tid; k <= Ub; k += NT) {
                         const int c = pcls[k];
                         int first = 1, nxt = -1;
                         for (int j = 0; j < k; ++j) if (pcls[j] == c) { first = 0; break; }
@@ -379,7 +450,7 @@ k3_grad(const float *__restrict__ logits, const int64_t *__restrict__ targets, i
                 mbar_wait(bar0 + 8 * stage, parity);
                 float *grow = grad + ((size_t)cc.b * T + cc.t) * V;
                 if (zero_rows) {
-                    zero_span(grow, (size_t)V, tid);
+                    zero_span<NT>(grow, (size_t)V, tid);
                     __syncthreads();
                     if (tid == 0 && issued < nrows) issue(stage);
                 } else {
@@ -391,19 +462,24 @@ k3_grad(const float *__restrict__ logits, const int64_t *__restrict__ targets, i
                     const float *gf = (const float *)(slot + slot_bytes);
                     const float lse2 = gf[1];
                     float4 *g4 = (float4 *)((uintptr_t)grow & ~(uintptr_t)15);
-                    // interior chunks 1..nch-2: aligned float4 in, aligned float4 out, no masking
+                    // interior chunks 1..nch-2: aligned float4 in, aligned float4 out, no masking.
+                    // All shared-memory loads are issued first so their latency is paid once per row.
+                    float4 xv[MAXC];
 #pragma unroll
                     for (int k = 0; k < MAXC; ++k) {
-                        const int c = 1 + tid + k * kStreamThreads;
-                        if (c <= nch - 2) {
-                            const float4 x = s4[c];
-                            float4 y;
-                            y.x = g * ex2f(fmaf(x.x, kLog2e, -lse2));
-                            y.y = g * ex2f(fmaf(x.y, kLog2e, -lse2));
-                            y.z = g * ex2f(fmaf(x.z, kLog2e, -lse2));
-                            y.w = g * ex2f(fmaf(x.w, kLog2e, -lse2));
-                            g4[c] = y;
-                        }
+                        const int c = 1 + tid + k * NT;
+                        if ((EXACT && k < MAXC - 1) || c <= nch - 2) xv[k] = s4[c];
+                        else xv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int k = 0; k < MAXC; ++k) {
+                        const int c = 1 + tid + k * NT;
+                        float4 y;
+                        y.x = g * ex2f(fmaf(xv[k].x, kLog2e, -lse2));
+                        y.y = g * ex2f(fmaf(xv[k].y, kLog2e, -lse2));
+                        y.z = g * ex2f(fmaf(xv[k].z, kLog2e, -lse2));
+                        y.w = g * ex2f(fmaf(xv[k].w, kLog2e, -lse2));
+                        if ((EXACT && k < MAXC - 1) || c <= nch - 2) g4[c] = y;
                     }
                     if (tid == 0 || (tid == 1 && nch > 1)) {   // the two edge chunks: scalar stores inside the row
                         const int c = tid == 0 ? 0 : nch - 1;
@@ -415,11 +491,12 @@ k3_grad(const float *__restrict__ logits, const int64_t *__restrict__ targets, i
                         if (e + 3 >= 0 && e + 3 < V) grow[e + 3] = g * ex2f(fmaf(x.w, kLog2e, -lse2));
                     }
                     // sparse occupancy correction for blank + first occurrence of each label
-                    float pv[2];
-                    int pc_[2];
+                    constexpr int MAXP = 256 / NT;         // U_b + 1 <= 256 patch slots
+                    float pv[MAXP];
+                    int pc_[MAXP];
 #pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
-                        const int k = tid + kk * kStreamThreads;
+                    for (int kk = 0; kk < MAXP; ++kk) {
+                        const int k = tid + kk * NT;
                         pc_[kk] = -1; pv[kk] = 0.f;
                         if (k <= Ub && pfirst[k]) {
                             float occ = 0.f;
@@ -432,37 +509,109 @@ k3_grad(const float *__restrict__ logits, const int64_t *__restrict__ targets, i
                     __syncthreads();                       // dense stores ordered before the patch; slot free
                     if (tid == 0 && issued < nrows) issue(stage);
 #pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) if (pc_[kk] >= 0) grow[pc_[kk]] = pv[kk];
+                    for (int kk = 0; kk < MAXP; ++kk) if (pc_[kk] >= 0) grow[pc_[kk]] = pv[kk];
                 }
                 cursor_next(cc, Tb_arr, B);
                 if (++stage == nst) { stage = 0; parity ^= 1; }
             }
         }
     }
-    {   // ---------------- phase B: padded frames ----------------
-        const int Zn = B * T - R;
-        if (Zn <= 0) return;
-        int z0, zc;
-        grid_share(Zn, z0, zc);
-        if (zc <= 0) return;
-        long long z = z0;
-        const long long z1 = (long long)z0 + zc;
-        int lo = 0, hi = B - 1;   // smallest b with pad-prefix(b+1) > z ; pad-prefix(b) = b*T - rowstart[b]
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if ((long long)(mid + 1) * T - rowstart[mid + 1] > z) hi = mid; else lo = mid + 1;
+    zero_padded_frames<NT>(grad, Tb_arr, rowstart, B, T, V, tid);   // phase B
+}
+
+// ------------------------------------------------------------------------------------------------
+// k3p: sparse occupancy correction after a FUSED sweep.  For every valid frame, the <= U_b+1 classes
+// that occur in the utterance get  grad[b,t,c] -= g_b * occupancy_t(c)  (one RED per class: repeated
+// labels are merged first through the per-utterance first/next table, so every address is touched
+// exactly once -> deterministic).  Frames of utterances without a valid alignment are overwritten with
+// zeros (zero_infinity) or NaN (torch's result).  Touches ~(U+1) 32-byte sectors per 17 KB frame.
+// ------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT)
+k3p_patch(const int64_t *__restrict__ targets, int64_t tnumel, const int *__restrict__ Tb_arr,
+          const int *__restrict__ Ub_arr, const int64_t *__restrict__ toff_arr, const int *__restrict__ flags,
+          const int *__restrict__ rowstart, const float *__restrict__ gam, float *__restrict__ grad,
+          int reduction, float inv_batch, int B, int T, int V, int Lp, int blank, int zero_inf) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    int *pcls = (int *)smem;                  // [Lp] class of patch slot k (0 = blank, k>=1: label k-1)
+    int *pnext = pcls + Lp;                   // [Lp] next slot with the same class, or -1
+    const int tid = threadIdx.x;
+    int r0, nrows;
+    grid_share(rowstart[B], r0, nrows);
+    if (nrows <= 0) return;
+    RowCursor cc;
+    cursor_seek(cc, r0, rowstart, Tb_arr, B);
+    constexpr int MAXP = 256 / NT;
+    int i = 0;
+    while (i < nrows) {                        // one utterance segment of this CTA's frame range per iteration
+        const int b = cc.b, t0 = cc.t;
+        const int seg = (cc.Tb - t0) < (nrows - i) ? (cc.Tb - t0) : (nrows - i);
+        const int Ub = Ub_arr[b];
+        const int infeasible = flags[b];
+        float *gbase = grad + ((size_t)b * T + t0) * V;
+        if (infeasible) {
+            if (zero_inf) zero_span<NT>(gbase, (size_t)seg * V, tid);
+            else fill_span<NT>(gbase, (size_t)seg * V, tid, __int_as_float(0x7fc00000));
+        } else {
+            const float g = reduction == 1 ? inv_batch * __frcp_rn((float)(Ub > 1 ? Ub : 1)) : 1.f;
+            const int64_t toff = toff_arr[b];
+            __syncthreads();                   // previous segment's table reads are done
+            for (int k = tid; k <= Ub; k += NT) {
+                long long c = blank;
+                if (k > 0) {
+                    const int64_t idx = toff + (k - 1);
+                    c = idx < tnumel ? targets[idx] : 0;
+                    c = c < 0 ? 0 : (c >= V ? V - 1 : c);
+                }
+                pcls[k] = (int)c;
+            }
+            __syncthreads();
+            int mycls[MAXP];
+            bool first[MAXP];
+#pragma unroll
+            for (int kk = 0; kk < MAXP; ++kk) {
+                const int k = tid + kk * NT;
+                mycls[kk] = -1; first[kk] = false;
+                if (k <= Ub) {
+                    const int c = pcls[k];
+                    int f = 1, nx = -1;
+                    for (int j = 0; j < k; ++j) if (pcls[j] == c) { f = 0; break; }
+                    for (int j = k + 1; j <= Ub; ++j) if (pcls[j] == c) { nx = j; break; }
+                    pnext[k] = nx; mycls[kk] = c; first[kk] = f;
+                }
+            }
+            __syncthreads();
+            const float *gf = gam + ((size_t)b * T + t0) * Lp;
+            const float ng = -g;
+#pragma unroll
+            for (int kk = 0; kk < MAXP; ++kk) {
+                if (!first[kk]) continue;
+                const int k = tid + kk * NT;
+                float *gp = gbase + mycls[kk];
+                const bool single = pnext[k] < 0;           // the common case: the class occurs once
+                const int off = k == 0 ? 0 : 3 + k;
+                int r = 0;
+                if (single) {                               // 16 frames in flight per thread (independent loads)
+                    for (; r + 16 <= seg; r += 16) {
+                        float o[16];
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) o[u] = __ldg(gf + (size_t)(r + u) * Lp + off);
+#pragma unroll
+                        for (int u = 0; u < 16; ++u)
+                            if (o[u] != 0.f) atomicAdd(gp + (size_t)(r + u) * V, ng * o[u]);   // RED: no return value
+                    }
+                }
+                for (; r < seg; ++r) {
+                    const float *f = gf + (size_t)r * Lp;
+                    float occ = 0.f;
+                    for (int j = k; j >= 0; j = pnext[j]) occ += (j == 0 ? f[0] : f[3 + j]);
+                    if (occ != 0.f) atomicAdd(gp + (size_t)r * V, ng * occ);
+                }
+            }
         }
-        int b = lo;
-        int t = Tb_arr[b] + (int)(z - ((long long)b * T - rowstart[b]));
-        while (z < z1) {
-            const long long run = (z1 - z) < (long long)(T - t) ? (z1 - z) : (long long)(T - t);
-            zero_span(grad + ((size_t)b * T + t) * V, (size_t)run * V, tid);
-            z += run;
-            ++b;
-            while (b < B && Tb_arr[b] >= T) ++b;
-            if (b >= B) break;
-            t = Tb_arr[b];
-        }
+        i += seg;
+        cc.t += seg - 1;
+        cursor_next(cc, Tb_arr, B);
     }
 }
 

@@ -92,8 +92,17 @@ def _side_streams(dev):
     return _SIDE[key]
 
 
+def _event_handle(ev):
+    """Raw cudaEvent_t of a torch event (created lazily by torch on first record: force it)."""
+    if ev is None:
+        return None
+    if not ev.cuda_event:
+        ev.record()                      # materialises the handle; re-recorded by the library on its stream
+    return ev.cuda_event
+
+
 def _n_chunks(B, requested):
-    n = requested if requested is not None else int(os.environ.get("CTCB200_CHUNKS", "4"))
+    n = requested if requested is not None else int(os.environ.get("CTCB200_CHUNKS", "1"))
     return max(1, min(int(n), B)) if B else 1
 
 
@@ -111,6 +120,7 @@ class _CTCLossB200Fn(torch.autograd.Function):
         L = _lib.lib()
         need_grad = ctx.needs_input_grad[0]
         fused = bool(need_grad and fused)
+        two_sweep = bool(int(os.environ.get("CTCB200_TWO_SWEEP", "1")))
         red = _RED[reduction]
         zi = int(bool(zero_infinity))
         inv_b = float(inv_batch) if inv_batch is not None else (1.0 / max(B, 1))
@@ -126,6 +136,7 @@ class _CTCLossB200Fn(torch.autograd.Function):
         ws_bytes = _lib.workspace_bytes(max(per, 1), T, V, umax)
         ws = torch.empty(n_ch * ws_bytes, dtype=torch.uint8, device=dev)
         one = torch.ones((), dtype=torch.float32, device=dev) if fused else None
+        sums = torch.zeros(n_ch, 3, dtype=torch.float32, device=dev)   # per chunk: [sum nll/U, sum nll, n]
         fwd = L.ctcb200_forward if need_grad else L.ctcb200_loss_only
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream()
@@ -136,19 +147,34 @@ class _CTCLossB200Fn(torch.autograd.Function):
                 side[0].wait_event(ev0)
                 side[1].wait_event(ev0)
             xs, ts, es = x.element_size() * T * V, 8, 4
+            prev_sweep = None
             for c in range(n_ch):
                 lo, hi = c * per, min((c + 1) * per, B)
                 n = hi - lo
                 if n <= 0:
                     break
                 st = side[c & 1].cuda_stream
+                # stagger: chunk c's sweep starts when chunk c-1's sweep is done, i.e. under c-1's lattice
+                sweep_ev = None
+                if n_ch > 1:
+                    if prev_sweep is not None:
+                        side[c & 1].wait_event(prev_sweep)
+                    sweep_ev = torch.cuda.Event()
+                    prev_sweep = sweep_ev
                 tgp = tg.data_ptr() + (lo * stride * ts if stride else 0)
                 wsp = ws.data_ptr() + c * ws_bytes
                 # 1-D targets: every chunk sees the whole concatenation and needs its own offset base;
                 # keep it simple and exact by running 1-D targets as a single chunk (see _prepare)
-                _lib.check(fwd(x.data_ptr() + lo * xs, tgp, stride, tg.numel() - lo * stride, il.data_ptr() + lo * 8,
-                               tl.data_ptr() + lo * 8, n, T, V, umax, int(blank), zi, nll.data_ptr() + lo * es,
-                               None, wsp, ws_bytes, st), "ctcb200_forward" if need_grad else "ctcb200_loss_only")
+                args = (x.data_ptr() + lo * xs, tgp, stride, tg.numel() - lo * stride, il.data_ptr() + lo * 8,
+                        tl.data_ptr() + lo * 8, n, T, V, umax, int(blank), zi)
+                if fused and two_sweep:
+                    _lib.check(L.ctcb200_loss_grad(*args, red, inv_b, nll.data_ptr() + lo * es, sums.data_ptr() + c * 12,
+                                                   grad.data_ptr() + lo * xs, wsp, ws_bytes, st,
+                                                   _event_handle(sweep_ev)), "ctcb200_loss_grad")
+                    continue
+                _lib.check(fwd(*args, nll.data_ptr() + lo * es, sums.data_ptr() + c * 12, wsp, ws_bytes, st,
+                               _event_handle(sweep_ev)),
+                           "ctcb200_forward" if need_grad else "ctcb200_loss_only")
                 if fused:
                     _lib.check(L.ctcb200_backward(x.data_ptr() + lo * xs, tgp, stride, tg.numel() - lo * stride,
                                                   one.data_ptr(), 0, red, inv_b, n, T, V, umax, int(blank), zi,
@@ -168,13 +194,12 @@ class _CTCLossB200Fn(torch.autograd.Function):
                 ctx.save_for_backward(grad)
             else:
                 ctx.save_for_backward(x, tg, ws)
-        if B == 0:
-            return nll if reduction == "none" else nll.sum()
         if reduction == "none":
             return nll
-        if reduction == "sum":
-            return nll.sum()
-        return (nll / tl.clamp(min=1).to(torch.float32)).sum() * inv_b
+        # the lattice kernel's last CTA of each chunk reduced its chunk in a fixed order (deterministic)
+        col = sums[:, 1] if reduction == "sum" else sums[:, 0]
+        tot = col[0] if n_ch == 1 else col.sum()
+        return tot if reduction == "sum" else tot * inv_b
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -222,7 +247,7 @@ def ctc_loss_b200(logits, targets, input_lengths, target_lengths, blank: int = 0
         otherwise).  This lets the gradient sweep of one chunk overlap the lattice of the next and
         is the default when the logits require grad (env CTCB200_FUSED=0 to disable); costs one
         extra [B,T,V] buffer held until backward, like autograd's own saved log-probs would.
-    chunks: utterance chunks of the two-stream pipeline (default env CTCB200_CHUNKS or 4).
+    chunks: utterance chunks of the two-stream pipeline (default env CTCB200_CHUNKS or 1).
     """
     if reduction not in _RED:
         raise ValueError(f"reduction must be one of {list(_RED)}")

@@ -3,10 +3,10 @@
 This is the call a host-side user of the op makes when the logits are not already on the device:
 the batch is cut into utterance chunks and pushed through a 3-stream pipeline
 
-    H2D(logits chunk i+1)  ||  prep + lse/gather + lattice + gradient kernels (chunk i)  ||  D2H(grad chunk i-1)
+    H2D(logits chunk i+1)  ||  prep + fused sweep + lattice + sparse patch kernels (chunk i)  ||  D2H(grad chunk i-1)
 
 so PCIe traffic in both directions overlaps the kernels.  All arithmetic is the same C-ABI calls
-(ctcb200_forward / ctcb200_backward) as the autograd op; torch supplies pinned/device memory,
+(ctcb200_loss_grad, the two-sweep path) as the autograd op; torch supplies pinned/device memory,
 streams and events.  Utterances are independent, so chunking does not change any result bit.
 """
 from __future__ import annotations
@@ -68,15 +68,11 @@ class HostCTCPipeline:
                 if i >= self.n_slots:
                     self.s_cmp.wait_event(self.ev_out[k])         # slot's previous grad has left
                 st = self.s_cmp.cuda_stream
-                _lib.check(L.ctcb200_forward(self.x[k].data_ptr(), self.tg[lo:hi].data_ptr(), self.tg.shape[1],
-                                             n * self.tg.shape[1], self.il[lo:hi].data_ptr(),
-                                             self.tl[lo:hi].data_ptr(), n, T, V, self.Umax, self.blank, self.zi,
-                                             self.nll[lo:hi].data_ptr(), None, self.ws[k].data_ptr(),
-                                             self.ws_bytes, st), "ctcb200_forward")
-                _lib.check(L.ctcb200_backward(self.x[k].data_ptr(), self.tg[lo:hi].data_ptr(), self.tg.shape[1],
-                                              n * self.tg.shape[1], self.one.data_ptr(), 0, red, 1.0 / B, n, T, V,
-                                              self.Umax, self.blank, self.zi, self.g[k].data_ptr(),
-                                              self.ws[k].data_ptr(), self.ws_bytes, st), "ctcb200_backward")
+                _lib.check(L.ctcb200_loss_grad(self.x[k].data_ptr(), self.tg[lo:hi].data_ptr(), self.tg.shape[1],
+                                               n * self.tg.shape[1], self.il[lo:hi].data_ptr(),
+                                               self.tl[lo:hi].data_ptr(), n, T, V, self.Umax, self.blank, self.zi,
+                                               red, 1.0 / B, self.nll[lo:hi].data_ptr(), None, self.g[k].data_ptr(),
+                                               self.ws[k].data_ptr(), self.ws_bytes, st, None), "ctcb200_loss_grad")
                 self.ev_cmp[k].record(self.s_cmp)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_cmp[k])

@@ -1,0 +1,43 @@
+"""Per-stage device timing of the two-sweep loss+grad call, for bench.py's roofline line.
+
+One un-chunked ``ctcb200_loss_grad`` call on the current stream, bracketed by CUDA events on that
+stream; the library's own ``sweep_done`` event (recorded right after the fused sweep kernel) splits the
+call into  [k0_prep + k1_lse_gather<FUSED>]  and  [k2_lattice + k3p_patch].
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .ctc import _RED, _prepare
+
+
+def time_stages(logits, targets, input_lengths, target_lengths, blank=0, reduction="mean",
+                zero_infinity=False, iters=10, warmup=3):
+    """Returns dict(sweep_ms=[...], rest_ms=[...]) with one entry per timed iteration."""
+    x, tg, stride, il, tl, B, T, V, umax = _prepare(logits.detach(), targets, input_lengths, target_lengths,
+                                                    blank, None)
+    L = _lib.lib()
+    ws_bytes = _lib.workspace_bytes(B, T, V, umax)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    nll = torch.empty(B, device=x.device)
+    sums = torch.zeros(3, device=x.device)
+    grad = torch.empty_like(x)
+    out = {"sweep_ms": [], "rest_ms": []}
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream()
+        for i in range(warmup + iters):
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e1.record(st)                                   # materialise the handle; re-recorded by the library
+            e0.record(st)
+            _lib.check(L.ctcb200_loss_grad(x.data_ptr(), tg.data_ptr(), stride, tg.numel(), il.data_ptr(),
+                                           tl.data_ptr(), B, T, V, umax, int(blank), int(bool(zero_infinity)),
+                                           _RED[reduction], 1.0 / max(B, 1), nll.data_ptr(), sums.data_ptr(),
+                                           grad.data_ptr(), ws.data_ptr(), ws_bytes, st.cuda_stream, e1.cuda_event),
+                       "ctcb200_loss_grad")
+            e2.record(st)
+            e2.synchronize()
+            if i >= warmup:
+                out["sweep_ms"].append(e0.elapsed_time(e1))
+                out["rest_ms"].append(e1.elapsed_time(e2))
+    return out

@@ -48,6 +48,7 @@ extern "C" {
 #define CTCB200_VERSION 100 /* 0.1.0 */
 
 typedef void *ctcb200_stream_t; /* cudaStream_t */
+typedef void *ctcb200_event_t;  /* cudaEvent_t  */
 
 enum ctcb200_error {
     CTCB200_OK = 0,
@@ -83,12 +84,15 @@ int ctcb200_workspace_bytes(int B, int T, int V, int Umax, size_t *out_bytes);
  * (the 2-element normaliser pair a data-parallel all-reduce combines).
  * Leaves the state occupancies in `workspace` for ctcb200_backward.
  * targets_stride: row stride of the [B,Umax] target matrix, or 0 for 1-D concatenated
- * targets (then targets_numel bounds the reads). */
+ * targets (then targets_numel bounds the reads).
+ * sweep_done: optional caller-owned event, recorded on `stream` right after the HBM-bound sweep
+ * (before the latency-bound lattice kernel) so that a caller pipelining several utterance chunks
+ * over two streams can start the next chunk's sweep under this chunk's lattice; NULL = none. */
 int ctcb200_forward(const float *logits, const int64_t *targets, int64_t targets_stride,
                     int64_t targets_numel, const int64_t *in_len, const int64_t *tgt_len,
                     int B, int T, int V, int Umax, int blank, int zero_infinity,
                     float *nll, float *loss_sums, void *workspace, size_t workspace_bytes,
-                    ctcb200_stream_t stream);
+                    ctcb200_stream_t stream, ctcb200_event_t sweep_done);
 
 /* Evaluation fast path (forward only, Trainer11.evaluate, trainer11.py:114-129): one sweep of
  * the logits; no occupancies are kept. Same outputs as ctcb200_forward. */
@@ -96,7 +100,7 @@ int ctcb200_loss_only(const float *logits, const int64_t *targets, int64_t targe
                       int64_t targets_numel, const int64_t *in_len, const int64_t *tgt_len,
                       int B, int T, int V, int Umax, int blank, int zero_infinity,
                       float *nll, float *loss_sums, void *workspace, size_t workspace_bytes,
-                      ctcb200_stream_t stream);
+                      ctcb200_stream_t stream, ctcb200_event_t sweep_done);
 
 /* Backward (replaces aten::_ctc_loss_backward + _log_softmax_backward_data):
  *   grad_logits[b,t,v] = g_b * (softmax(logits)[b,t,v] - occupancy[b,t,v]),  0 for t >= in_len[b].
@@ -109,6 +113,20 @@ int ctcb200_backward(const float *logits, const int64_t *targets, int64_t target
                      int reduction, float inv_batch, int B, int T, int V, int Umax, int blank,
                      int zero_infinity, float *grad_logits, const void *workspace,
                      size_t workspace_bytes, ctcb200_stream_t stream);
+
+/* Loss AND gradient in TWO sweeps of [B,T,V] instead of three (the fast path of the autograd op).
+ * The sweep that computes the log-softmax statistics also writes the dense part of the gradient,
+ * g_b * softmax(logits), from the registers that hold the row; after the lattice a sparse kernel adds
+ * -g_b * occupancy to the <= U_b+1 label columns of each frame and zero/NaN-fills utterances without
+ * a valid alignment.  g_b is computed for an upstream gradient of 1:
+ * g_b = (reduction==MEAN ? inv_batch / max(U_b,1) : 1); use ctcb200_rescale_grad afterwards if the
+ * real upstream gradient differs.  Same outputs as ctcb200_forward + ctcb200_backward(grad_out=1). */
+int ctcb200_loss_grad(const float *logits, const int64_t *targets, int64_t targets_stride,
+                      int64_t targets_numel, const int64_t *in_len, const int64_t *tgt_len,
+                      int B, int T, int V, int Umax, int blank, int zero_infinity, int reduction,
+                      float inv_batch, float *nll, float *loss_sums, float *grad_logits,
+                      void *workspace, size_t workspace_bytes, ctcb200_stream_t stream,
+                      ctcb200_event_t sweep_done);
 
 /* Speculative-gradient support.  A caller that wants loss AND gradient from one pass may run
  * ctcb200_backward right after ctcb200_forward with grad_out == 1 (before autograd has produced the

@@ -53,7 +53,7 @@ def test_argument_validation_precedes_cuda(lib):
     def call(**kw):
         a = dict(ok, **kw)
         return f(a["logits"], a["targets"], a["ts"], a["tn"], a["il"], a["tl"], a["B"], a["T"], a["V"], a["U"],
-                 a["blank"], a["zi"], a["nll"], a["sums"], a["ws"], a["wsb"], a["stream"])
+                 a["blank"], a["zi"], a["nll"], a["sums"], a["ws"], a["wsb"], a["stream"], None)
 
     assert call(logits=None) == -1
     assert call(V=1) == -2

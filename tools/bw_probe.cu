@@ -39,12 +39,52 @@ __global__ void __launch_bounds__(128) probe(const float *__restrict__ in, float
         mbar_wait(bar0 + 8 * stage, parity);
         const float4 *s4 = (const float4 *)(smem + (size_t)stage * slot_bytes);
         float4 *o4 = (float4 *)(out + (size_t)row_of(i) * V);
-        for (int c = tid; c < nch; c += 128) {
-            float4 x = s4[c];
-            if (op) { x.x *= 1.5f; x.y *= 1.5f; x.z *= 1.5f; x.w *= 1.5f; o4[c] = x; }
-            else acc += x.x + x.y + x.z + x.w;
+        if (op <= 1) {
+            for (int c = tid; c < nch; c += 128) {
+                float4 x = s4[c];
+                if (op) { x.x *= 1.5f; x.y *= 1.5f; x.z *= 1.5f; x.w *= 1.5f; o4[c] = x; }
+                else acc += x.x + x.y + x.z + x.w;
+            }
+            __syncthreads();
+        } else {
+            // k1-like: row in registers, max, (op>=3: block reduce + barrier), exp-sum (op 2,4: MUFU; op 3: FADD only)
+            __shared__ float red[2][8];
+            float4 v[9];
+            float mx = -1e30f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const int c = tid + 128 * k;
+                v[k] = c < nch ? s4[c] : make_float4(-1e30f, -1e30f, -1e30f, -1e30f);
+                mx = fmaxf(mx, fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w)));
+            }
+            float *rd = red[i & 1];
+            if (op >= 3) {
+                mx = warp_max(mx);
+                if ((tid & 31) == 0) rd[tid >> 5] = mx;
+            }
+            __syncthreads();
+            if (tid == 0 && issued < n) {
+                mbar_expect_tx(bar0 + 8 * stage, rb);
+                tma_load_1d(slot0 + stage * slot_bytes, in + (size_t)row_of(issued) * V, rb, bar0 + 8 * stage);
+                ++issued;
+            }
+            if (op >= 3) mx = fmaxf(fmaxf(rd[0], rd[1]), fmaxf(rd[2], rd[3]));
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                if (op == 3) sum += (v[k].x - mx) + (v[k].y - mx) + (v[k].z - mx) + (v[k].w - mx);
+                else sum += ex2f(v[k].x - mx) + ex2f(v[k].y - mx) + ex2f(v[k].z - mx) + ex2f(v[k].w - mx);
+            }
+            if (op >= 3) {
+                sum = warp_sum(sum);
+                if ((tid & 31) == 0) rd[4 + (tid >> 5)] = sum;
+                __syncthreads();
+                sum = rd[4] + rd[5] + rd[6] + rd[7];
+            }
+            acc += sum;
+            if (++stage == nst) { stage = 0; parity ^= 1; }
+            continue;
         }
-        __syncthreads();
         if (tid == 0 && issued < n) {
             mbar_expect_tx(bar0 + 8 * stage, rb);
             tma_load_1d(slot0 + stage * slot_bytes, in + (size_t)row_of(issued) * V, rb, bar0 + 8 * stage);
@@ -76,17 +116,20 @@ int main(int argc, char **argv) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const uint32_t slot = (V * 4 + 127) / 128 * 128;
     auto time_it = [&](auto launch) { for (int i = 0; i < 3; ++i) launch(); cudaEventRecord(e0); for (int i = 0; i < 10; ++i) launch(); cudaEventRecord(e1); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); return ms / 10; };
-    for (int op = 0; op < 2; ++op) {
-        float ms = time_it([&] { plain_copy<<<sms * 8, 512>>>((const float4 *)in, (float4 *)out, n / 4, op, sink); });
-        printf("plain %s: %.1f us  %.0f GB/s\n", op ? "copy" : "read", ms * 1e3, (op ? 2 : 1) * n * 4 / ms / 1e6);
-        for (int cps : {2, 3, 4}) for (int nst : {3, 4, 6}) {
+    const char *opname[] = {"read", "copy", "read+max+ex2 (1 barrier)", "read+max+reduce+add (2 barriers, no MUFU)", "read+k1-like (2 barriers, MUFU)"};
+    for (int op = 0; op < 5; ++op) {
+        if (op < 2) {
+            float ms = time_it([&] { plain_copy<<<sms * 8, 512>>>((const float4 *)in, (float4 *)out, n / 4, op, sink); });
+            printf("plain %s: %.1f us  %.0f GB/s\n", op ? "copy" : "read", ms * 1e3, (op ? 2 : 1) * n * 4 / ms / 1e6);
+        }
+        for (int cps : {3, 4}) for (int nst : {3}) {
             size_t smem = (size_t)nst * slot + 8 * nst;
             if (smem * cps > 225 * 1024) continue;
             cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            for (int mode = 0; mode < 3; ++mode) {
+            for (int mode = 0; mode < 1; ++mode) {
                 int R = 8;
                 float ms2 = time_it([&] { probe<<<sms * cps, 128, smem>>>(in, out, sink, rows, V, mode, R, op, nst, slot); });
-                printf("  tma-ring %s cps=%d nst=%d mode=%d: %.1f us  %.0f GB/s\n", op ? "copy" : "read", cps, nst, mode, ms2 * 1e3, (op ? 2 : 1) * n * 4 / ms2 / 1e6);
+                printf("  tma-ring %s cps=%d nst=%d mode=%d: %.1f us  %.0f GB/s\n", opname[op], cps, nst, mode, ms2 * 1e3, (op == 1 ? 2 : 1) * n * 4 / ms2 / 1e6);
             }
         }
     }

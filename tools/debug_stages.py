@@ -45,7 +45,7 @@ def main(B=5, T=37, V=53, Umax=9, seed=1, zi=0, dist="D1"):
     sums = torch.zeros(3, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     rc = L.ctcb200_forward(x.data_ptr(), tg.data_ptr(), tg.shape[1], tg.numel(), il.data_ptr(), tl.data_ptr(),
-                           B, T, V, Umax, 0, zi, nll.data_ptr(), sums.data_ptr(), ws.data_ptr(), wsb, st)
+                           B, T, V, Umax, 0, zi, nll.data_ptr(), sums.data_ptr(), ws.data_ptr(), wsb, st, None)
     print("forward rc", rc, _lib.strerror(rc)); torch.cuda.synchronize()
     w = ws.cpu().numpy()
     i32 = lambda name, n: w[off[name]: off[name] + 4 * n].view(np.int32)
