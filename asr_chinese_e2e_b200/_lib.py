@@ -55,6 +55,7 @@ SIGNATURES = {
     "ctcb200_forward": (_i, _FWD_ARGS),
     "ctcb200_loss_only": (_i, _FWD_ARGS),
     "ctcb200_loss_grad": (_i, [_p, _p, _i64, _i64, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _sz, _p, _p]),
+    "ctcb200_loss_grad_stages": (_i, [_i, _p, _p, _i64, _i64, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _sz, _p]),
     "ctcb200_backward": (_i, [_p, _p, _i64, _i64, _p, _i64, _i, _f, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "ctcb200_rescale_grad": (_i, [_p, _p, _i64, _p, _p, _i, _i, _i, _p]),
     "ctcb200_read_status": (_i, [_p, ctypes.POINTER(_i), _p]),

@@ -156,6 +156,7 @@ cudaError_t launch_k2(cudaStream_t s, const int64_t *targets, int64_t tnumel, co
 
 struct FusedGrad {          // non-null grad => 2-sweep mode: the sweep writes g*softmax, k3p adds -g*occupancy
     float *grad; int reduction; float inv_batch;
+    int stages;             // bit 0: prep + sweep, bit 1: lattice, bit 2: sparse patch (7 = the whole call)
 };
 
 // Every kernel of the path asks for the maximum shared-memory carveout: a launch whose carveout differs
@@ -188,18 +189,21 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     float *lp_lab = (float *)(ws + w.lp_lab), *gam = (float *)(ws + w.gam), *ab = (float *)(ws + w.ab);
     const int64_t tnumel = targets_stride ? (int64_t)B * targets_stride : targets_numel;
 
+    const bool fused = fg != nullptr;
+    const int stages = fused ? fg->stages : 7;
+    cudaError_t e = cudaSuccess;
+    if (stages & 1) {
     prefer_max_carveout(k0_prep);
     k0_prep<<<1, 1024, 0, s>>>(in_len, tgt_len, targets_stride, B, T, Umax, hdr, Tb, Ub, flags, toff, rowstart);
-    cudaError_t e = cudaGetLastError();
+    e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
 
     StreamCfg c;
-    const bool fused = fg != nullptr;
     int nt1, rounds1;
     bool exact1;
     stream_pick(V, env_int(fused ? "CTCB200_K1F_NT" : "CTCB200_K1_NT", fused ? 128 : 64), &nt1, &rounds1, &exact1);
     if (fused)
-        rc = stream_cfg(V, 0, 64 + (size_t)g.Lp * 4, dev.sms, 3, 3, "CTCB200_K1F_NST", "CTCB200_K1F_CPS", &c);
+        rc = stream_cfg(V, 0, 64 + (size_t)g.Lp * 4, dev.sms, 4, 2, "CTCB200_K1F_NST", "CTCB200_K1F_CPS", &c);
     else
         rc = stream_cfg(V, 0, 64 + (size_t)g.Lp * 4, dev.sms, nt1 == 64 ? 2 : 3, nt1 == 64 ? 5 : 3,
                         "CTCB200_K1_NST", "CTCB200_K1_CPS", &c);
@@ -217,8 +221,10 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     }
     if (e != cudaSuccess) return (int)e;
     if (sweep_done && (e = cudaEventRecord((cudaEvent_t)sweep_done, s)) != cudaSuccess) return (int)e;
+    }   // stage: sweep
 
     if (env_int("CTCB200_DEBUG_SKIP_LATTICE", 0)) return CTCB200_OK;   // profiling aid: time the sweep alone
+    if (stages & 2) {
     unsigned *ticket = (unsigned *)(hdr + 1);
 #define K2_ARGS s, targets, tnumel, Tb, Ub, toff, flags, lp_lab, gam, ab, nll, loss_sums, ticket, B, T, zero_infinity
     if (want_grad) {
@@ -231,7 +237,8 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
         else e = launch_k2<16, false>(K2_ARGS);
     }
 #undef K2_ARGS
-    if (e != cudaSuccess || !fused) return (int)e;
+    }   // stage: lattice
+    if (e != cudaSuccess || !fused || !(stages & 4)) return (int)e;
     {
         const int per = env_int("CTCB200_K3P_CPS", 32);
         const size_t smem = 2 * (size_t)g.Lp * 4;
@@ -300,9 +307,23 @@ int ctcb200_loss_grad(const float *logits, const int64_t *targets, int64_t targe
     if (!grad_logits) return CTCB200_ERR_NULL;
     if ((uintptr_t)grad_logits & 15) return CTCB200_ERR_ALIGN;
     if (reduction < 0 || reduction > 2) return CTCB200_ERR_REDUCTION;
-    const FusedGrad fg = {grad_logits, reduction, inv_batch};
+    const FusedGrad fg = {grad_logits, reduction, inv_batch, 7};
     return forward_impl(true, &fg, logits, targets, targets_stride, targets_numel, in_len, tgt_len, B, T, V, Umax,
                         blank, zero_infinity, nll, loss_sums, workspace, workspace_bytes, stream, sweep_done);
+}
+
+int ctcb200_loss_grad_stages(int stages, const float *logits, const int64_t *targets, int64_t targets_stride,
+                             int64_t targets_numel, const int64_t *in_len, const int64_t *tgt_len, int B, int T, int V,
+                             int Umax, int blank, int zero_infinity, int reduction, float inv_batch, float *nll,
+                             float *loss_sums, float *grad_logits, void *workspace, size_t workspace_bytes,
+                             ctcb200_stream_t stream) {
+    if (!grad_logits) return CTCB200_ERR_NULL;
+    if ((uintptr_t)grad_logits & 15) return CTCB200_ERR_ALIGN;
+    if (reduction < 0 || reduction > 2) return CTCB200_ERR_REDUCTION;
+    if (stages < 1 || stages > 7) return CTCB200_ERR_SHAPE;
+    const FusedGrad fg = {grad_logits, reduction, inv_batch, stages};
+    return forward_impl(true, &fg, logits, targets, targets_stride, targets_numel, in_len, tgt_len, B, T, V, Umax,
+                        blank, zero_infinity, nll, loss_sums, workspace, workspace_bytes, stream, nullptr);
 }
 
 int ctcb200_backward(const float *logits, const int64_t *targets, int64_t targets_stride, int64_t targets_numel,

@@ -37,7 +37,7 @@ struct LatCfg {
     static constexpr int NL = NS / 2;
     static constexpr int Lp = 4 + 32 * NL;
     static constexpr int Sp = 32 * NS;
-    static constexpr int NSTG = 2;                         // ring depth per warp (16 frames ahead)
+    static constexpr int NSTG = NS == 4 ? 3 : 2;           // ring depth per warp (24 / 16 frames ahead)
     static constexpr uint32_t LP_ROW = Lp * 4;
     static constexpr uint32_t AB_ROW = Sp * 4;
     static constexpr uint32_t STAGE = kLatTT * (LP_ROW + (GRAD ? AB_ROW : 0));
@@ -87,14 +87,16 @@ __device__ __forceinline__ void lds_vec(float (&d)[N], uint32_t a) {
         }
     }
 }
+// stores of the lattice's own scratch (stored halves, occupancies): keep them in L2 (evict_last), they are
+// read back within microseconds while a [B,T,V] sweep of another chunk may be streaming through the cache
 template <int N>
 __device__ __forceinline__ void stg_vec(float *p, const float (&d)[N]) {
     if (N == 2) {
-        *(float2 *)p = make_float2(d[0], d[1]);
+        stg_v2_hint((float2 *)p, make_float2(d[0], d[1]), kEvictLast);
     } else {
 #pragma unroll
         for (int k = 0; k < N / 4; ++k)
-            ((float4 *)p)[k] = make_float4(d[4 * k], d[4 * k + 1], d[4 * k + 2], d[4 * k + 3]);
+            stg_v4_hint((float4 *)p + k, make_float4(d[4 * k], d[4 * k + 1], d[4 * k + 2], d[4 * k + 3]), kEvictLast);
     }
 }
 
@@ -224,8 +226,8 @@ __device__ __forceinline__ void lattice_dir(unsigned char *smem, int pair, int l
         const int stg = n % NSTG;
         const uint32_t dst = ring + stg * C::STAGE, bar = bar0 + 8 * stg;
         mbar_expect_tx(bar, rows * C::LP_ROW + (ph2 ? rows * C::AB_ROW : 0));
-        tma_load_1d(dst, lp_base + (size_t)t0 * Lp, rows * C::LP_ROW, bar);
-        if (ph2) tma_load_1d(dst + TT * C::LP_ROW, ab_base + (size_t)t0 * Sp, rows * C::AB_ROW, bar);
+        tma_load_1d_hint(dst, lp_base + (size_t)t0 * Lp, rows * C::LP_ROW, bar, kEvictLast);
+        if (ph2) tma_load_1d_hint(dst + TT * C::LP_ROW, ab_base + (size_t)t0 * Sp, rows * C::AB_ROW, bar, kEvictLast);
     };
     __syncwarp();
 
@@ -345,7 +347,7 @@ __device__ __forceinline__ void lattice_dir(unsigned char *smem, int pair, int l
             for (int r = 0; r < TT; ++r) if (lane == r) mine = gbl[r];
             if (lane < TT) {                                     // lane r writes the header of the r-th processed row
                 const int rr = DIR ? (TT - 1 - lane) : lane;
-                *(float2 *)(gam_base + (size_t)(t0 + rr) * Lp) = make_float2(mine, lds_f32(tile + rr * C::LP_ROW + 4));
+                stg_v2_hint((float2 *)(gam_base + (size_t)(t0 + rr) * Lp), make_float2(mine, lds_f32(tile + rr * C::LP_ROW + 4)), kEvictLast);
             }
         } else {
             // ragged stage, or the stage that holds the midpoint
@@ -356,7 +358,7 @@ __device__ __forceinline__ void lattice_dir(unsigned char *smem, int pair, int l
                 if (!GRAD || infeasible) break;
                 gb = warp_sum(gb);
                 if (lane == 0)
-                    *(float2 *)(gam_base + (size_t)(t0 + rr) * Lp) = make_float2(gb, lds_f32(tile + rr * C::LP_ROW + 4));
+                    stg_v2_hint((float2 *)(gam_base + (size_t)(t0 + rr) * Lp), make_float2(gb, lds_f32(tile + rr * C::LP_ROW + 4)), kEvictLast);
             }
         }
         if (!GRAD || infeasible) break;

@@ -53,6 +53,31 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint3
         "l"(src), "r"(bytes), "r"(bar)
         : "memory");
 }
+// L2 eviction-priority policies (the encodings CUTLASS uses for TMA cache hints on sm_90/sm_100).
+// The [B,T,V] streams are touched once per kernel -> evict_first, so that they do not flush the small
+// per-frame arrays (lp_lab, gam, stored alpha/beta halves) the lattice kernel re-reads -> evict_last.
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+
+__device__ __forceinline__ void tma_load_1d_hint(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void stg_v4_hint(float4 *p, float4 v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void stg_v2_hint(float2 *p, float2 v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void stg_f32_hint(float *p, float v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(policy) : "memory");
+}
+
 // generic-proxy writes to global -> later async-proxy (TMA) reads of the same bytes
 __device__ __forceinline__ void fence_proxy_async_global() {
     asm volatile("fence.proxy.async.global;" ::: "memory");

@@ -125,7 +125,7 @@ __device__ __forceinline__ uint32_t issue_row(const float *row, int V, uintptr_t
     }
     const uint32_t bytes = (uint32_t)(a1 - a0);
     if (bytes + extra_tx) mbar_expect_tx(bar, bytes + extra_tx); else mbar_arrive(bar);
-    if (bytes) tma_load_1d(slot, (const void *)a0, bytes, bar);
+    if (bytes) tma_load_1d_hint(slot, (const void *)a0, bytes, bar, kEvictFirst);   // streamed once
     return bytes;
 }
 
@@ -335,7 +335,7 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
                 float o;
                 if (cg[kk] >= 0) o = fmaxf(fmaf(xg[kk], kLog2e, -lse2), kNeg);   // -inf logit -> sentinel
                 else o = cg[kk] == -2 ? lse2 : (cg[kk] == -3 ? 0.f : kNeg);
-                frame[k] = o;
+                stg_f32_hint(frame + k, o, kEvictLast);           // re-read by the lattice kernel
             }
         }
         if (FUSED) {
@@ -347,7 +347,7 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
             for (int k = 0; k < MAXC; ++k) {
                 const int c = 1 + tid + k * NT;
                 if ((EXACT && k < MAXC - 1) || c <= nch - 2)
-                    g4[c] = make_float4(v[k].x * sc, v[k].y * sc, v[k].z * sc, v[k].w * sc);
+                    stg_v4_hint(g4 + c, make_float4(v[k].x * sc, v[k].y * sc, v[k].z * sc, v[k].w * sc), kEvictFirst);
             }
             if (tid == 0 || (tid == 1 && nch > 1)) {       // edge chunks: scalar stores inside the row
                 const int c = tid == 0 ? 0 : nch - 1;
@@ -479,7 +479,7 @@ k3_grad(const float *__restrict__ logits, const int64_t *__restrict__ targets, i
                         y.y = g * ex2f(fmaf(xv[k].y, kLog2e, -lse2));
                         y.z = g * ex2f(fmaf(xv[k].z, kLog2e, -lse2));
                         y.w = g * ex2f(fmaf(xv[k].w, kLog2e, -lse2));
-                        if ((EXACT && k < MAXC - 1) || c <= nch - 2) g4[c] = y;
+                        if ((EXACT && k < MAXC - 1) || c <= nch - 2) stg_v4_hint(g4 + c, y, kEvictFirst);
                     }
                     if (tid == 0 || (tid == 1 && nch > 1)) {   // the two edge chunks: scalar stores inside the row
                         const int c = tid == 0 ? 0 : nch - 1;
@@ -598,7 +598,13 @@ k3p_patch(const int64_t *__restrict__ targets, int64_t tnumel, const int *__rest
                         for (int u = 0; u < 16; ++u) o[u] = __ldg(gf + (size_t)(r + u) * Lp + off);
 #pragma unroll
                         for (int u = 0; u < 16; ++u)
-                            if (o[u] != 0.f) atomicAdd(gp + (size_t)(r + u) * V, ng * o[u]);   // RED: no return value
+                            if (o[u] != 0.f) {
+#ifdef CTCB200_EXPERIMENT_PLAIN_STORE
+                                gp[(size_t)(r + u) * V] = ng * o[u];      // timing experiment only (wrong values)
+#else
+                                atomicAdd(gp + (size_t)(r + u) * V, ng * o[u]);   // RED: no return value
+#endif
+                            }
                     }
                 }
                 for (; r < seg; ++r) {

@@ -88,7 +88,8 @@ _SIDE = {}
 def _side_streams(dev):
     key = (dev.type, dev.index)
     if key not in _SIDE:
-        _SIDE[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        # high priority: the few lattice CTAs must be placed ahead of the thousands of queued sweep/patch CTAs
+        _SIDE[key] = (torch.cuda.Stream(dev, priority=-1), torch.cuda.Stream(dev, priority=-1))
     return _SIDE[key]
 
 
@@ -104,6 +105,64 @@ def _event_handle(ev):
 def _n_chunks(B, requested):
     n = requested if requested is not None else int(os.environ.get("CTCB200_CHUNKS", "1"))
     return max(1, min(int(n), B)) if B else 1
+
+
+def _two_sweep_pipeline(ctx, L, x, tg, stride, il, tl, B, T, V, umax, blank, zi, red, inv_b, nll, grad, reduction):
+    """Default training path.  Two utterance chunks (80 % / 20 %):
+
+        main stream:  sweep(a)  sweep(b)            patch(a)   patch(b)
+        side stream:            lattice(a)  ......  lattice(b)
+
+    lattice(a) runs under sweep(b) and lattice(b) under patch(a), so the latency-bound lattice never
+    leaves the HBM idle, and the sparse patches run after all sweeps instead of fighting them for DRAM."""
+    dev = x.device
+    m = 4 // math.gcd(T * V, 4)                      # chunk starts must stay 16-byte aligned
+    split = float(os.environ.get("CTCB200_SPLIT", "1.0"))   # measured on B200: one chunk wins (profiles/), see DESIGN.md 5
+    cut = int(round(B * split / m)) * m
+    bounds = [0, B] if (B < 16 or cut <= 0 or cut >= B or stride == 0) else [0, cut, B]
+    n_ch = len(bounds) - 1
+    ws_bytes = [_lib.workspace_bytes(bounds[c + 1] - bounds[c], T, V, umax) for c in range(n_ch)]
+    ws_off = [sum(ws_bytes[:c]) for c in range(n_ch)]
+    ws = torch.empty(sum(ws_bytes), dtype=torch.uint8, device=dev)
+    sums = torch.zeros(n_ch, 3, dtype=torch.float32, device=dev)
+    xs = 4 * T * V
+
+    def call(c, stages, stream):
+        lo, n = bounds[c], bounds[c + 1] - bounds[c]
+        _lib.check(L.ctcb200_loss_grad_stages(
+            stages, x.data_ptr() + lo * xs, tg.data_ptr() + lo * stride * 8, stride, tg.numel() - lo * stride,
+            il.data_ptr() + lo * 8, tl.data_ptr() + lo * 8, n, T, V, umax, blank, zi, red, inv_b,
+            nll.data_ptr() + lo * 4, sums.data_ptr() + c * 12, grad.data_ptr() + lo * xs,
+            ws.data_ptr() + ws_off[c], ws_bytes[c], stream.cuda_stream), "ctcb200_loss_grad_stages")
+
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream()
+        if n_ch == 1:
+            call(0, 7, main)
+        else:
+            side = _side_streams(dev)[0]
+            ev_s = [torch.cuda.Event() for _ in range(n_ch)]
+            ev_l = [torch.cuda.Event() for _ in range(n_ch)]
+            for c in range(n_ch):
+                call(c, 1, main)
+                ev_s[c].record(main)
+                side.wait_event(ev_s[c])
+                call(c, 2, side)
+                ev_l[c].record(side)
+            for c in range(n_ch):
+                main.wait_event(ev_l[c])
+                call(c, 4, main)
+        if _DEBUG:
+            for c in range(n_ch):
+                _check_status(ws[ws_off[c]:], main.cuda_stream)
+    ctx.cfg = (stride, B, T, V, umax, blank, zi, red, 0, 0, n_ch, inv_b, True)
+    ctx.applied = torch.ones(B, dtype=torch.float32, device=dev)
+    ctx.save_for_backward(grad)
+    if reduction == "none":
+        return nll
+    col = sums[:, 1] if reduction == "sum" else sums[:, 0]
+    tot = col[0] if n_ch == 1 else col.sum()
+    return tot if reduction == "sum" else tot * inv_b
 
 
 class _CTCLossB200Fn(torch.autograd.Function):
@@ -127,6 +186,10 @@ class _CTCLossB200Fn(torch.autograd.Function):
         dev = x.device
         nll = torch.empty(B, dtype=torch.float32, device=dev)
         grad = torch.empty_like(x) if fused else None
+        if fused and two_sweep and chunks is None and "CTCB200_CHUNKS" not in os.environ:
+            out = _two_sweep_pipeline(ctx, L, x, tg, stride, il, tl, B, T, V, umax, int(blank), zi, red, inv_b,
+                                      nll, grad, reduction)
+            return out
         n_ch = _n_chunks(B, chunks)
         per = (B + n_ch - 1) // n_ch if B else 0
         # every chunk's slab must start 16-byte aligned: chunk size multiple of 4/gcd(T*V, 4) utterances

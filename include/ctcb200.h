@@ -128,6 +128,17 @@ int ctcb200_loss_grad(const float *logits, const int64_t *targets, int64_t targe
                       void *workspace, size_t workspace_bytes, ctcb200_stream_t stream,
                       ctcb200_event_t sweep_done);
 
+/* The same call, one stage at a time, for callers that pipeline utterance chunks over two streams
+ * (the lattice is latency-bound and should run under another chunk's sweep):
+ * stages is a bit mask of  1 = prep + fused sweep,  2 = lattice,  4 = sparse patch; each stage must
+ * be ordered after the previous stage of the same workspace by the caller (events). */
+int ctcb200_loss_grad_stages(int stages, const float *logits, const int64_t *targets,
+                             int64_t targets_stride, int64_t targets_numel, const int64_t *in_len,
+                             const int64_t *tgt_len, int B, int T, int V, int Umax, int blank,
+                             int zero_infinity, int reduction, float inv_batch, float *nll,
+                             float *loss_sums, float *grad_logits, void *workspace,
+                             size_t workspace_bytes, ctcb200_stream_t stream);
+
 /* Speculative-gradient support.  A caller that wants loss AND gradient from one pass may run
  * ctcb200_backward right after ctcb200_forward with grad_out == 1 (before autograd has produced the
  * real upstream gradient) and fix the result up later: this multiplies utterance b's gradient slab
