@@ -7,7 +7,7 @@ libctcb200.so is missing -- there is no CPU fallback.
 """
 from .ctc import CTCLossB200, ctc_loss_b200  # noqa: F401
 from .joint import JointCTCAttention, Pack  # noqa: F401
-from .sharded import combine_sharded_mean, sharded_ctc_loss  # noqa: F401
+from .sharded import combine_equal_shards, combine_sharded_mean, sharded_ctc_loss  # noqa: F401
 
-__all__ = ["CTCLossB200", "ctc_loss_b200", "JointCTCAttention", "Pack", "combine_sharded_mean",
+__all__ = ["CTCLossB200", "ctc_loss_b200", "JointCTCAttention", "Pack", "combine_equal_shards", "combine_sharded_mean",
            "sharded_ctc_loss"]

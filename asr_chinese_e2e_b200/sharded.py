@@ -5,8 +5,9 @@ collective.  The only exchange is ONE all-reduce of the 2-element buffer
 ``[sum_b nll_b / max(U_b,1), B_local]`` (NCCL over NVLink on GPUs, gloo in the CPU tests); the global
 'mean' loss is ``buf[0] / buf[1]``.  The returned tensor has the GLOBAL value and a LOCAL gradient:
 d loss / d logits_local = 1 / (B_global * U_b) * (softmax - occupancy), which is what a DDP
-all-reduce of parameter gradients (sum) then expects.  The division by B_global stays on the
-device (no host sync), so the gradient sweep is enqueued right behind the collective.
+all-reduce of parameter gradients (sum) then expects.  With equal shards (the reference's
+drop_last=True) 1/B_global is known before the kernels run, so the op's upstream gradient is exactly 1
+and nothing waits on the collective; nothing ever syncs with the host.
 
 The reference has no multi-process path at all (its only multi-GPU construct is a disabled
 nn.DataParallel wrapper, Predictor/Bases/base_model.py:9-21, main.py:80).
@@ -18,22 +19,43 @@ import torch.distributed as dist
 
 
 def combine_sharded_mean(local_sum: torch.Tensor, local_count: int, group=None) -> torch.Tensor:
-    """local_sum: differentiable scalar sum_b nll_b/max(U_b,1) over this rank's shard."""
+    """General form (shards may differ in size).  local_sum: differentiable scalar
+    sum_b nll_b/max(U_b,1) over this rank's shard.  No host sync: the count travels as a device scalar."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local_sum / float(max(local_count, 1))
-    buf = torch.stack([local_sum.detach().to(torch.float32),
-                       torch.tensor(float(local_count), device=local_sum.device)])
+    buf = torch.empty(2, dtype=torch.float32, device=local_sum.device)
+    buf[0] = local_sum.detach()
+    buf[1].fill_(float(local_count))
     dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     inv = 1.0 / buf[1].clamp(min=1.0)
     local = local_sum * inv                                   # gradient flows through this term only
     return local + (buf[0] * inv - local.detach())            # value: global mean
 
 
+def combine_equal_shards(local_contrib: torch.Tensor, group=None) -> torch.Tensor:
+    """Equal shard sizes (drop_last=True, as the reference's loader: data/data_loader/ai_shell_1.py:103):
+    local_contrib = sum_b nll_b/U_b / B_global is already this rank's share of the global mean, so the
+    upstream gradient of the op stays exactly 1 (no rescale sweep) and the collective is one all-reduce
+    of a single float, enqueued behind the kernels with no host sync."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local_contrib
+    tot = local_contrib.detach().clone()
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    return local_contrib + (tot - local_contrib.detach())     # value: global mean; gradient: d/d local = 1
+
+
 def sharded_ctc_loss(logits, targets, input_lengths, target_lengths, blank: int = 0,
-                     zero_infinity: bool = False, group=None, max_target_length=None):
+                     zero_infinity: bool = False, group=None, max_target_length=None, equal_shards: bool = True):
     """'mean'-reduced CTC loss over the GLOBAL batch; call on every rank with its own shard."""
     from .ctc import ctc_loss_b200
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    B = logits.shape[0]
+    if equal_shards:
+        local = ctc_loss_b200(logits, targets, input_lengths, target_lengths, blank=blank, reduction="mean",
+                              zero_infinity=zero_infinity, inv_batch=1.0 / max(world * B, 1),
+                              max_target_length=max_target_length)
+        return combine_equal_shards(local, group)
     local_sum = ctc_loss_b200(logits, targets, input_lengths, target_lengths, blank=blank,
                               reduction="mean", zero_infinity=zero_infinity, inv_batch=1.0,
                               max_target_length=max_target_length)
-    return combine_sharded_mean(local_sum, logits.shape[0], group)
+    return combine_sharded_mean(local_sum, B, group)

@@ -14,7 +14,7 @@ from oracle.synth import make_case
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from asr_chinese_e2e_b200.sharded import combine_sharded_mean
+    from asr_chinese_e2e_b200.sharded import combine_equal_shards, combine_sharded_mean
     c = make_case(6, 24, 19, 5, 99)
     h = 3
     sl = slice(rank * h, (rank + 1) * h)
@@ -23,7 +23,13 @@ def _worker(rank, world, port, q):
                      c["target_lengths"][sl], reduction="none")       # oracle stands in for the CUDA op
     local_sum = (nll / c["target_lengths"][sl].clamp(min=1)).sum()
     loss = combine_sharded_mean(local_sum, h)
-    loss.backward()
+    loss.backward(retain_graph=True)
+    g_general = x.grad.clone()
+    x.grad = None
+    loss2 = combine_equal_shards(local_sum / (world * h))     # equal shards: 1/B_global folded in up front
+    loss2.backward()
+    assert abs(loss2.item() - loss.item()) < 1e-5 * abs(loss.item())
+    assert torch.allclose(x.grad, g_general, atol=1e-7)
     q.put((rank, loss.item(), x.grad.clone()))
     dist.barrier()
     dist.destroy_process_group()
