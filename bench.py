@@ -38,8 +38,8 @@ UNIT = "utt/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lengths", default="var", choices=["var", "full"])
     ap.add_argument("--no-e2e", action="store_true")
@@ -62,7 +62,10 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms.  Started before the warm-up so that it is
+    already running when the (short) timed region begins; summary() keeps the samples whose arrival time
+    falls inside the timed window and, if the window was shorter than one sampling period, falls back to
+    the samples taken under the same load during warm-up + timed steps (and says so)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -73,7 +76,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -83,30 +86,43 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def wait_first_sample(self, timeout=5.0):
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
 
     def __exit__(self, *a):
         if self.proc:
-            time.sleep(0.25)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
 
-    def summary(self):
-        sm, mx, reasons = [], 0.0, set()
+    def summary(self, t0, t1, load_t0):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+
+        def digest(rows):
+            sm, mx, reasons = [], 0.0, set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                except (ValueError, IndexError):
+                    continue
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            return sm, mx, reasons
+        window = "timed region"
+        rows = [x for x in self.rows if t0 <= x[0] <= t1 + 0.06]
+        if not digest(rows)[0]:
+            rows = [x for x in self.rows if load_t0 <= x[0] <= t1 + 0.06]
+            window = "warm-up + timed region (timed region shorter than one 50 ms sampling period)"
+        sm, mx, reasons = digest(rows)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_reference_line(args, c, steps, warmup):
@@ -202,20 +218,25 @@ def main():
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     K = args.steps
-    for _ in range(max(args.warmup, 3)):
-        loss = step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    # ---- headline: K steps of the public op (chunked two-stream pipeline, gradient fused into forward) ----
+    # ---- headline: K steps of the public op (two-sweep path, gradient produced in the forward call) ----
     with ClockSampler(local) as clocks:
+        clocks.wait_first_sample()
+        load_t0 = time.time()
+        for _ in range(max(args.warmup, 3)):
+            loss = step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
         t_start, t_end = ev(), ev()
+        wall0 = time.time()
         t_start.record()
         for i in range(K):
             loss = step()
         t_end.record()
         torch.cuda.synchronize()
+        wall1 = time.time()
+        clock_summary = clocks.summary(wall0, wall1, load_t0)
     total_ms = t_start.elapsed_time(t_end)
     if world > 1:
         t = torch.tensor([total_ms], device=dev)
@@ -229,7 +250,7 @@ def main():
     #      two-sweep call; the library's sweep_done event splits it into [k0_prep + fused sweep kernel]
     #      and [lattice + sparse patch] ----
     from asr_chinese_e2e_b200.profiling import time_stages
-    st = time_stages(x, tg, il, tl, reduction="mean", zero_infinity=False, iters=K, warmup=3)
+    st = time_stages(x, tg, il, tl, reduction="mean", zero_infinity=False, iters=min(K, 50), warmup=3)
     sweep_ms, rest_ms = statistics.mean(st["sweep_ms"]), statistics.mean(st["rest_ms"])
 
     n_chunks = int(os.environ.get("CTCB200_CHUNKS", "1"))
@@ -264,7 +285,7 @@ def main():
                               "pipeline": f"{n_chunks} utterance chunk(s), two-sweep path, gradient produced in the "
                                           "forward call (speculative upstream gradient 1)",
                               "sweep_ms": sweep_ms, "lattice_plus_patch_ms": rest_ms},
-            "clocks": clocks.summary()}
+            "clocks": clock_summary}
 
     if rank == 0 and world == 1:
         if not args.no_e2e:
