@@ -124,10 +124,17 @@ class JointCTCAttention:
         if output.ctc_logits is None:          # Pack returns None for a missing key (pack.py:7-8)
             raise KeyError("output Pack has no 'ctc_logits': forward() must add the CTC head output")
         att = attention_ce(output.pred, output.gold, getattr(self, "att_smoothing", 0.0))
-        ctc = ctc_loss_b200(output.ctc_logits.float(), input.tgt_for_input, input.wave_len, input.tgt_len,
-                            blank=IGNORE_ID, reduction="mean", zero_infinity=self.ctc_zero_infinity)
         w = self.ctc_weight
-        return w * ctc + (1.0 - w) * att, ctc, att
+        B = output.ctc_logits.shape[0]
+        # ctc_weight is folded into the op's normaliser (inv_batch = w/B): the op returns w*ctc and its
+        # speculative gradient is already the final one, so backward() costs one empty launch instead of a
+        # rescaling sweep over [B,T,V]
+        wctc = ctc_loss_b200(output.ctc_logits.float(), input.tgt_for_input, input.wave_len, input.tgt_len,
+                             blank=IGNORE_ID, reduction="mean", zero_infinity=self.ctc_zero_infinity,
+                             inv_batch=(w if w > 0 else 1.0) / max(B, 1))
+        if w > 0:
+            return wctc + (1.0 - w) * att, wctc / w, att
+        return att + 0.0 * wctc, wctc, att
 
     def cal_metrics(self, output, input):
         loss, ctc, att = self.joint_loss(output, input)

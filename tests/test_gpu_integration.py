@@ -1,0 +1,106 @@
+"""GPU: the callers either side of the kernels -- joint CTC/attention mix-in with the real op, the
+host-buffer pipeline, the stage-split C ABI, the sharded wrapper on one rank."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle.synth import make_case
+from oracle.torch_ref import ref_ctc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_joint_mixin_on_gpu_matches_torch_autograd():
+    from tiny_model import TinyJoint, _batch
+    torch.manual_seed(3)
+    m = TinyJoint().cuda()
+    batch = _batch().to("cuda")
+    out = m.forward(batch)
+    met = m.cal_metrics(out, batch)
+    met.loss.backward()
+    got = {k: p.grad.clone() for k, p in m.named_parameters()}
+    m.zero_grad()
+    # reference: identical graph with torch's own CTC on the same device
+    out = m.forward(batch)
+    ctc = F.ctc_loss(F.log_softmax(out.ctc_logits, -1).transpose(0, 1), batch.tgt_for_input, batch.wave_len,
+                     batch.tgt_len, blank=0, reduction="mean", zero_infinity=True)
+    att = F.cross_entropy(out.pred.reshape(-1, out.pred.size(-1)), out.gold.reshape(-1), ignore_index=0)
+    ref = 0.3 * ctc + 0.7 * att
+    ref.backward()
+    assert abs(met.loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert abs(met.ctc_loss.item() - ctc.item()) <= 1e-5 * abs(ctc.item())
+    for k, p in m.named_parameters():
+        assert torch.allclose(got[k], p.grad, rtol=1e-3, atol=1e-5), k
+
+
+def test_host_pipeline_matches_oracle():
+    from asr_chinese_e2e_b200.host_pipeline import ctc_loss_grad_host
+    c = make_case(11, 48, 4234 // 8, 9, 31, dist="D2", n_infeasible=1, n_partial=1)
+    loss, nll, grad = ctc_loss_grad_host(c["logits"], c["targets"], c["input_lengths"], c["target_lengths"],
+                                         reduction="mean", zero_infinity=True, chunk=4)
+    rl, rg = ref_ctc(c["logits"], c["targets"], c["input_lengths"], c["target_lengths"], reduction="mean",
+                     zero_infinity=True)
+    assert abs(loss.item() - rl.item()) <= 1e-5 * abs(rl.item())
+    assert (grad - rg).abs().max().item() <= 1e-4
+
+
+def test_stage_split_abi_equals_single_call():
+    from asr_chinese_e2e_b200 import _lib
+    L = _lib.lib()
+    c = make_case(9, 40, 133, 7, 5, dist="D1", n_infeasible=1)
+    x = c["logits"].cuda()
+    tg, il, tl = c["targets"].cuda(), c["input_lengths"].cuda(), c["target_lengths"].cuda()
+    B, T, V = x.shape
+    U = tg.shape[1]
+    wsb = _lib.workspace_bytes(B, T, V, U)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run(stage_list):
+        ws = torch.zeros(wsb, dtype=torch.uint8, device="cuda")
+        nll = torch.empty(B, device="cuda"); sums = torch.zeros(3, device="cuda"); grad = torch.full_like(x, 7.0)
+        for stg in stage_list:
+            rc = L.ctcb200_loss_grad_stages(stg, x.data_ptr(), tg.data_ptr(), U, tg.numel(), il.data_ptr(),
+                                            tl.data_ptr(), B, T, V, U, 0, 1, 1, 1.0 / B, nll.data_ptr(),
+                                            sums.data_ptr(), grad.data_ptr(), ws.data_ptr(), wsb, st)
+            assert rc == 0, _lib.strerror(rc)
+        torch.cuda.synchronize()
+        return nll, sums, grad
+    a = run([7])
+    b = run([1, 2, 4])
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    rl, rg = ref_ctc(c["logits"], c["targets"], c["input_lengths"], c["target_lengths"], reduction="mean",
+                     zero_infinity=True)
+    assert (a[2].cpu() - rg).abs().max().item() <= 1e-4
+    assert abs(a[1][0].item() / B - rl.item()) <= 1e-5 * abs(rl.item())
+    assert L.ctcb200_loss_grad_stages(0, *([None] * 2), 0, 0, None, None, 1, 1, 5, 1, 0, 0, 1, 1.0, None, None,
+                                      ctypes.c_void_p(16), None, 0, None) != 0
+
+
+def test_sharded_wrapper_single_rank_and_debug_status():
+    from asr_chinese_e2e_b200 import _lib, sharded_ctc_loss
+    c = make_case(6, 30, 41, 6, 17)
+    x = c["logits"].cuda().requires_grad_(True)
+    loss = sharded_ctc_loss(x, c["targets"].cuda(), c["input_lengths"].cuda(), c["target_lengths"].cuda())
+    loss.backward()
+    rl, rg = ref_ctc(c["logits"], c["targets"], c["input_lengths"], c["target_lengths"], reduction="mean")
+    assert abs(loss.item() - rl.item()) <= 1e-5 * abs(rl.item())
+    assert (x.grad.cpu() - rg).abs().max().item() <= 1e-4
+    # invalid inputs are clamped and reported through the device status word (debug API)
+    L = _lib.lib()
+    B, T, V = x.shape
+    tg = c["targets"].clone(); tg[0, 0] = V + 5                      # label out of range
+    il = c["input_lengths"].clone(); il[1] = T + 3                   # input length out of range
+    tgc, ilc, tlc = tg.cuda(), il.cuda(), c["target_lengths"].cuda()
+    wsb = _lib.workspace_bytes(B, T, V, tg.shape[1])
+    ws = torch.zeros(wsb, dtype=torch.uint8, device="cuda"); nll = torch.empty(B, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    assert L.ctcb200_forward(x.data_ptr(), tgc.data_ptr(), tg.shape[1], tg.numel(), ilc.data_ptr(), tlc.data_ptr(),
+                             B, T, V, tg.shape[1], 0, 1, nll.data_ptr(), None, ws.data_ptr(), wsb, st, None) == 0
+    status = ctypes.c_int(0)
+    assert L.ctcb200_read_status(ws.data_ptr(), ctypes.byref(status), st) == 0
+    assert status.value & 1 and status.value & 4
+    assert torch.isfinite(nll[2:]).all()

@@ -18,9 +18,15 @@ from asr_chinese_e2e_b200.joint import attention_ce, edit_distance, greedy_ctc_i
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def oracle_ctc(logits, targets, il, tl, blank=0, reduction="mean", zero_infinity=False, **kw):
-    return F.ctc_loss(F.log_softmax(logits, -1).transpose(0, 1), targets, il, tl, blank=blank,
-                      reduction=reduction, zero_infinity=zero_infinity)
+def oracle_ctc(logits, targets, il, tl, blank=0, reduction="mean", zero_infinity=False, inv_batch=None, **kw):
+    nll = F.ctc_loss(F.log_softmax(logits, -1).transpose(0, 1), targets, il, tl, blank=blank,
+                     reduction="none", zero_infinity=zero_infinity)
+    if reduction == "none":
+        return nll
+    if reduction == "sum":
+        return nll.sum()
+    inv = inv_batch if inv_batch is not None else 1.0 / logits.shape[0]      # same contract as ctc_loss_b200
+    return (nll / tl.clamp(min=1)).sum() * inv
 
 
 def test_pack_semantics():
@@ -63,43 +69,7 @@ def test_attention_ce_matches_reference_formulation():
     assert torch.allclose(attention_ce(pred, gold, eps), want, atol=1e-6)
 
 
-class TinyEnc(torch.nn.Module):
-    def __init__(self, d_in, d):
-        super().__init__()
-        self.p = torch.nn.Linear(d_in, d)
-
-    def forward(self, wave, wave_len):
-        mask = (torch.arange(wave.size(1))[None, :] < wave_len[:, None]).unsqueeze(-1).float()
-        return (torch.tanh(self.p(wave)) * mask,)      # padded frames zeroed like the reference encoder
-
-
-class TinyDec(torch.nn.Module):
-    def __init__(self, d, V):
-        super().__init__()
-        self.emb, self.out = torch.nn.Embedding(V, d), torch.nn.Linear(d, V)
-
-    def forward(self, tgt, enc, lens):
-        B = tgt.size(0)
-        ys = torch.cat([torch.full((B, 1), 2), tgt], 1)                  # <sos> + tokens
-        gold = torch.cat([tgt, torch.zeros(B, 1, dtype=torch.long)], 1)
-        for b, n in enumerate(lens.tolist()):
-            gold[b, n] = 3                                               # <eos>
-        return self.out(self.emb(ys) + enc.mean(1, keepdim=True)), gold
-
-
-class TinyJoint(JointCTCAttention, torch.nn.Module):
-    def __init__(self, V=13, d=16):
-        torch.nn.Module.__init__(self)
-        self.encoder, self.decoder = TinyEnc(8, d), TinyDec(d, V)
-        self.init_ctc(d, V, ctc_weight=0.3, ctc_zero_infinity=True)
-
-
-def _batch(B=3, T=12, U=4, V=13):
-    g = torch.Generator().manual_seed(5)
-    tl = torch.tensor([4, 2, 3])
-    tg = torch.randint(4, V, (B, U), generator=g) * (torch.arange(U)[None] < tl[:, None])
-    return Pack(wave=torch.randn(B, T, 8, generator=g), wave_len=torch.tensor([12, 9, 7]),
-                tgt_for_input=tg, tgt_len=tl)
+from tiny_model import TinyJoint, _batch  # noqa: E402
 
 
 def test_joint_mixin_wiring(monkeypatch):
