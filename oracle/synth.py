@@ -69,7 +69,7 @@ def random_alignment(tg_row, u, t_len, gen):
         gap = 1 if (k > 0 and tg_row[k] == tg_row[k - 1]) else 0
         base += gap
         p = base + cuts[k]
-        out[p] = int(tg_row[k])
+        out[min(p, t_len - 1)] = int(tg_row[k])
         base += 1
     return out
 

@@ -104,3 +104,52 @@ def test_sharded_wrapper_single_rank_and_debug_status():
     assert L.ctcb200_read_status(ws.data_ptr(), ctypes.byref(status), st) == 0
     assert status.value & 1 and status.value & 4
     assert torch.isfinite(nll[2:]).all()
+
+
+def test_no_out_of_bounds_writes_guard_zones():
+    """compute-sanitizer is closed on the GPU pool, so the write side is checked with canaries: every
+    output buffer (grad, nll, loss_sums, workspace) is carved out of a larger poisoned allocation and the
+    guard zones on both sides must be bit-identical after the two-sweep and the three-sweep calls.
+    V=37 and an odd B*T make every row misaligned and the tensor end not 16-byte aligned."""
+    from asr_chinese_e2e_b200 import _lib
+    L = _lib.lib()
+    c = make_case(5, 23, 37, 6, 11, dist="D2", n_infeasible=1)
+    x = c["logits"].cuda()
+    tg, il, tl = c["targets"].cuda(), c["input_lengths"].cuda(), c["target_lengths"].cuda()
+    B, T, V = x.shape
+    U = tg.shape[1]
+    wsb = _lib.workspace_bytes(B, T, V, U)
+    G = 4096                                                   # guard bytes (multiple of 256)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def guarded(nbytes):
+        raw = torch.full((G + nbytes + G,), 0xA5, dtype=torch.uint8, device="cuda")
+        return raw, raw[G:G + nbytes]
+
+    for mode in ("two_sweep", "three_sweep", "loss_only"):
+        graw, gbuf = guarded(B * T * V * 4)
+        nraw, nbuf = guarded(B * 4)
+        sraw, sbuf = guarded(3 * 4)
+        wraw, wbuf = guarded(wsb)
+        assert gbuf.data_ptr() % 16 == 0 and wbuf.data_ptr() % 256 == 0
+        if mode == "two_sweep":
+            rc = L.ctcb200_loss_grad(x.data_ptr(), tg.data_ptr(), U, tg.numel(), il.data_ptr(), tl.data_ptr(), B, T, V, U,
+                                     0, 1, 1, 1.0 / B, nbuf.data_ptr(), sbuf.data_ptr(), gbuf.data_ptr(), wbuf.data_ptr(),
+                                     wsb, st, None)
+        else:
+            f = L.ctcb200_forward if mode == "three_sweep" else L.ctcb200_loss_only
+            rc = f(x.data_ptr(), tg.data_ptr(), U, tg.numel(), il.data_ptr(), tl.data_ptr(), B, T, V, U, 0, 1,
+                   nbuf.data_ptr(), sbuf.data_ptr(), wbuf.data_ptr(), wsb, st, None)
+            if rc == 0 and mode == "three_sweep":
+                one = torch.ones((), device="cuda")
+                rc = L.ctcb200_backward(x.data_ptr(), tg.data_ptr(), U, tg.numel(), one.data_ptr(), 0, 1, 1.0 / B, B, T, V,
+                                        U, 0, 1, gbuf.data_ptr(), wbuf.data_ptr(), wsb, st)
+        assert rc == 0, _lib.strerror(rc)
+        torch.cuda.synchronize()
+        for name, raw, n in (("grad", graw, B * T * V * 4), ("nll", nraw, B * 4), ("sums", sraw, 12), ("ws", wraw, wsb)):
+            assert bool((raw[:G] == 0xA5).all()) and bool((raw[G + n:] == 0xA5).all()), f"{mode}: {name} guard zone written"
+        if mode != "loss_only":
+            grad = gbuf.view(torch.float32).view(B, T, V)
+            _, rg = ref_ctc(c["logits"], c["targets"], c["input_lengths"], c["target_lengths"], reduction="mean",
+                            zero_infinity=True)
+            assert (grad.cpu() - rg).abs().max().item() <= 1e-4, mode
