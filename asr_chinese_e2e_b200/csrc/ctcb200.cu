@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#include "ce_kernel.cuh"
 #include "lattice_kernel.cuh"
 #include "layout.h"
 #include "stream_kernels.cuh"
@@ -251,6 +252,26 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     return (int)e;
 }
 
+
+template <int NT, int MAXC, bool EXACT>
+cudaError_t launch_kce(const StreamCfg &c, cudaStream_t s, bool want_grad, const float *pred, const int64_t *gold,
+                       int rows, int V, const int *hdr, const int *vlist, const int *plist, float *rowloss,
+                       float *grad, float eps, float weight) {
+    cudaError_t e;
+    if (want_grad) {
+        e = cudaFuncSetAttribute(kce_rows<NT, MAXC, EXACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+        if (e != cudaSuccess) return e;
+        kce_rows<NT, MAXC, EXACT, true><<<c.grid, NT, c.smem, s>>>(pred, gold, rows, V, hdr, vlist, plist, rowloss, grad,
+                                                                   eps, weight, c.nst, c.slot_bytes);
+    } else {
+        e = cudaFuncSetAttribute(kce_rows<NT, MAXC, EXACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+        if (e != cudaSuccess) return e;
+        kce_rows<NT, MAXC, EXACT, false><<<c.grid, NT, c.smem, s>>>(pred, gold, rows, V, hdr, vlist, plist, rowloss, grad,
+                                                                    eps, weight, c.nst, c.slot_bytes);
+    }
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 extern "C" {
@@ -382,6 +403,56 @@ int ctcb200_rescale_grad(float *grad_logits, const float *grad_out, int64_t grad
     prefer_max_carveout(k4_rescale);
     k4_rescale<<<dim3(per, B), 256, 0, (cudaStream_t)stream>>>(grad_logits, grad_out, grad_out_stride, applied_in,
                                                                  applied_out, T, V);
+    return (int)cudaGetLastError();
+}
+
+// ---- attention-branch cross-entropy -------------------------------------------
+static size_t ce_ws_layout(int64_t rows, size_t *o_vlist, size_t *o_plist, size_t *o_rowloss) {
+    size_t o = kAlign;                      // hdr
+    *o_vlist = o;   o += align_up(sizeof(int) * (size_t)(rows > 0 ? rows : 1));
+    *o_plist = o;   o += align_up(sizeof(int) * (size_t)(rows > 0 ? rows : 1));
+    *o_rowloss = o; o += align_up(sizeof(float) * (size_t)(rows > 0 ? rows : 1));
+    return o;
+}
+
+int ctcb200_ce_workspace_bytes(int64_t rows, size_t *out_bytes) {
+    if (!out_bytes) return CTCB200_ERR_NULL;
+    if (rows < 0 || rows > 0x7fffffff) return CTCB200_ERR_SHAPE;
+    size_t a, b, c;
+    *out_bytes = ce_ws_layout(rows, &a, &b, &c);
+    return CTCB200_OK;
+}
+
+int ctcb200_ce_loss_grad(const float *pred, const int64_t *gold, int64_t rows, int V, int ignore_index,
+                         float smoothing, float weight, float *loss_out, float *grad, void *workspace,
+                         size_t workspace_bytes, ctcb200_stream_t stream) {
+    if (!pred || !gold || !loss_out || !workspace) return CTCB200_ERR_NULL;
+    if (rows < 0 || rows > 0x7fffffff || V < 2 || V > kMaxV || smoothing < 0.f || smoothing >= 1.f) return CTCB200_ERR_SHAPE;
+    if (((uintptr_t)pred & 15) || ((uintptr_t)grad & 15) || ((uintptr_t)workspace & 255)) return CTCB200_ERR_ALIGN;
+    size_t o_v, o_p, o_r;
+    if (workspace_bytes < ce_ws_layout(rows, &o_v, &o_p, &o_r)) return CTCB200_ERR_WORKSPACE;
+    if (rows == 0) return CTCB200_OK;
+    DevInfo dev;
+    int rc = device_info(&dev);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned char *ws = (unsigned char *)workspace;
+    int *hdr = (int *)ws, *vlist = (int *)(ws + o_v), *plist = (int *)(ws + o_p);
+    float *rowloss = (float *)(ws + o_r);
+    prefer_max_carveout(kce_prep);
+    kce_prep<<<1, 1024, 0, s>>>(gold, (int)rows, ignore_index, hdr, vlist, plist);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    StreamCfg c;
+    int nt, rounds;
+    bool exact;
+    stream_pick(V, 128, &nt, &rounds, &exact);
+    if ((rc = stream_cfg(V, 0, 128, dev.sms, grad ? 4 : 3, grad ? 2 : 4, "CTCB200_CE_NST", "CTCB200_CE_CPS", &c))) return rc;
+    e = STREAM_DISPATCH(launch_kce, 128, rounds, exact, c, s, grad != nullptr, pred, gold, (int)rows, V, hdr, vlist, plist,
+                        rowloss, grad, smoothing, weight);
+    if (e != cudaSuccess) return (int)e;
+    prefer_max_carveout(kce_finish);
+    kce_finish<<<1, 1024, 0, s>>>(hdr, vlist, rowloss, weight, loss_out);
     return (int)cudaGetLastError();
 }
 

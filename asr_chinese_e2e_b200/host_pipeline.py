@@ -17,16 +17,19 @@ from . import _lib
 
 
 class HostCTCPipeline:
-    def __init__(self, B, T, V, Umax, chunk=32, device="cuda", blank=0, zero_infinity=False, n_slots=3):
+    def __init__(self, B, T, V, Umax, chunk=32, device="cuda", blank=0, zero_infinity=False, n_slots=3,
+                 grad_to_host=True):
         self.B, self.T, self.V, self.Umax = B, T, V, Umax
         self.chunk = min(chunk, B)
         self.blank, self.zi = int(blank), int(bool(zero_infinity))
         self.dev = torch.device(device)
         self.n_slots = n_slots
+        self.grad_to_host = grad_to_host          # False: the gradient stays on the device (self.g_full)
         c = self.chunk
         self.ws_bytes = _lib.workspace_bytes(c, T, V, Umax)
         self.x = [torch.empty(c, T, V, device=self.dev) for _ in range(n_slots)]
-        self.g = [torch.empty(c, T, V, device=self.dev) for _ in range(n_slots)]
+        self.g_full = None if grad_to_host else torch.empty(B, T, V, device=self.dev)
+        self.g = [torch.empty(c, T, V, device=self.dev) for _ in range(n_slots)] if grad_to_host else None
         self.ws = [torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.dev) for _ in range(n_slots)]
         self.tg = torch.empty(B, max(Umax, 1), dtype=torch.int64, device=self.dev)
         self.il = torch.empty(B, dtype=torch.int64, device=self.dev)
@@ -38,7 +41,7 @@ class HostCTCPipeline:
         self.ev_cmp = [torch.cuda.Event() for _ in range(n_slots)]
         self.ev_out = [torch.cuda.Event() for _ in range(n_slots)]
         self.h2d_bytes = B * T * V * 4 + self.tg.numel() * 8 + 2 * B * 8
-        self.d2h_bytes = B * T * V * 4 + B * 4
+        self.d2h_bytes = (B * T * V * 4 if grad_to_host else 0) + B * 4
         self.launches_per_step = 4 * ((B + self.chunk - 1) // self.chunk)
 
     def __call__(self, h_logits, h_targets, h_il, h_tl, h_grad, h_nll, reduction="mean"):
@@ -65,19 +68,21 @@ class HostCTCPipeline:
                 self.ev_in[k].record(self.s_in)
             with torch.cuda.stream(self.s_cmp):
                 self.s_cmp.wait_event(self.ev_in[k])
-                if i >= self.n_slots:
+                if i >= self.n_slots and self.grad_to_host:
                     self.s_cmp.wait_event(self.ev_out[k])         # slot's previous grad has left
+                gdst = self.g[k] if self.grad_to_host else self.g_full[lo:hi]
                 st = self.s_cmp.cuda_stream
                 _lib.check(L.ctcb200_loss_grad(self.x[k].data_ptr(), self.tg[lo:hi].data_ptr(), self.tg.shape[1],
                                                n * self.tg.shape[1], self.il[lo:hi].data_ptr(),
                                                self.tl[lo:hi].data_ptr(), n, T, V, self.Umax, self.blank, self.zi,
-                                               red, 1.0 / B, self.nll[lo:hi].data_ptr(), None, self.g[k].data_ptr(),
+                                               red, 1.0 / B, self.nll[lo:hi].data_ptr(), None, gdst.data_ptr(),
                                                self.ws[k].data_ptr(), self.ws_bytes, st, None), "ctcb200_loss_grad")
                 self.ev_cmp[k].record(self.s_cmp)
-            with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(self.ev_cmp[k])
-                h_grad[lo:hi].copy_(self.g[k][:n], non_blocking=True)
-                self.ev_out[k].record(self.s_out)
+            if self.grad_to_host:
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(self.ev_cmp[k])
+                    h_grad[lo:hi].copy_(self.g[k][:n], non_blocking=True)
+                    self.ev_out[k].record(self.s_out)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_stream(self.s_cmp)
             h_nll.copy_(self.nll, non_blocking=True)

@@ -23,6 +23,7 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
+from .ce import attention_ce_b200
 from .ctc import ctc_loss_b200
 
 IGNORE_ID = 0   # PAD id of the reference vocab == CTC blank (Predictor/Utils/loss.py:5, vocab.py:10)
@@ -123,8 +124,13 @@ class JointCTCAttention:
     def joint_loss(self, output, input):
         if output.ctc_logits is None:          # Pack returns None for a missing key (pack.py:7-8)
             raise KeyError("output Pack has no 'ctc_logits': forward() must add the CTC head output")
-        att = attention_ce(output.pred, output.gold, getattr(self, "att_smoothing", 0.0))
         w = self.ctc_weight
+        eps = getattr(self, "att_smoothing", 0.0)
+        if output.pred.is_cuda and w < 1.0:
+            # attention branch on the same sweep kernels, (1-w) folded in (no rescaling sweep in backward)
+            att = attention_ce_b200(output.pred.float(), output.gold, eps, weight=1.0 - w) / (1.0 - w)
+        else:
+            att = attention_ce(output.pred, output.gold, eps)
         B = output.ctc_logits.shape[0]
         # ctc_weight is folded into the op's normaliser (inv_batch = w/B): the op returns w*ctc and its
         # speculative gradient is already the final one, so backward() costs one empty launch instead of a

@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=64, help="utterances in the CPU-baseline sample")
     ap.add_argument("--vocab", type=int, default=V_, help="developer experiments only (default = BASELINE V)")
+    ap.add_argument("--shape", default=None, help="developer experiments only: B,T,U (default = BASELINE C2 256,400,50)")
     return ap.parse_args()
 
 
@@ -177,8 +178,10 @@ def workload_cfg(args, n):
 
 def main():
     args = parse()
-    global V_
+    global V_, B_, T_, U_
     V_ = args.vocab
+    if args.shape:
+        B_, T_, U_ = (int(v) for v in args.shape.split(","))
     if args.impl == "reference":
         return run_reference(args)
 
@@ -290,6 +293,8 @@ def main():
     if rank == 0 and world == 1:
         if not args.no_e2e:
             line["e2e"] = run_e2e(torch, c, args, dev)
+            # the training-shaped variant: the gradient's consumer is the next GPU kernel, only the loss goes back
+            line["e2e_grad_on_device"] = run_e2e(torch, c, args, dev, grad_to_host=False)
         if not args.no_cpu:
             cb = cpu_reference_line(args, c, steps=5, warmup=2)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -309,10 +314,10 @@ def main():
         dist.destroy_process_group()
 
 
-def run_e2e(torch, c, args, dev):
+def run_e2e(torch, c, args, dev, grad_to_host=True):
     """Host-buffer API: pinned logits -> device, kernels, gradient + nll -> pinned host, every step."""
     from asr_chinese_e2e_b200.host_pipeline import HostCTCPipeline
-    pipe = HostCTCPipeline(B_, T_, V_, U_, chunk=32, device=dev)
+    pipe = HostCTCPipeline(B_, T_, V_, U_, chunk=32, device=dev, grad_to_host=grad_to_host)
     h_x = c["logits"].pin_memory()
     h_tg, h_il, h_tl = c["targets"].pin_memory(), c["input_lengths"].pin_memory(), c["target_lengths"].pin_memory()
     h_g = torch.empty(B_, T_, V_, pin_memory=True)
@@ -329,8 +334,9 @@ def run_e2e(torch, c, args, dev):
     loss = float((h_n / h_tl.clamp(min=1).float()).mean())
     return {"value": B_ / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
             "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": ms, "steps": k, "loss": loss,
-            "api": "asr_chinese_e2e_b200.host_pipeline.HostCTCPipeline (pinned host logits in; grad[B,T,V] + "
-                   "nll[B] back to pinned host; 3-stream chunked pipeline, chunk=32 utterances)",
+            "api": "asr_chinese_e2e_b200.host_pipeline.HostCTCPipeline (pinned host logits in; "
+                   + ("grad[B,T,V] + " if grad_to_host else "gradient left on the device, ")
+                   + "nll[B] back to pinned host; 3-stream chunked pipeline, chunk=32 utterances)",
             "gpu_launches_per_step": pipe.launches_per_step}
 
 

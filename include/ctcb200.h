@@ -149,6 +149,18 @@ int ctcb200_rescale_grad(float *grad_logits, const float *grad_out, int64_t grad
                          const float *applied_in, float *applied_out, int B, int T, int V,
                          ctcb200_stream_t stream);
 
+/* Attention-branch loss on the same sweep machinery: cross-entropy with optional label
+ * smoothing over pred[rows, V] logits, rows whose gold == ignore_index skipped -- the reference's
+ * cal_loss / calculate_loss (Predictor/Utils/loss.py:26-76; called with pred [N,T,C] flattened, PAD=0):
+ *   smoothing == 0: F.cross_entropy(pred, gold, ignore_index, 'mean')
+ *   smoothing  > 0: target = (1-eps) on the label and eps/V elsewhere; sum_rows(-sum_c target*logp) / n_word
+ * loss_out[2] = { weight * loss, n_word }.  If grad != NULL the same sweep writes
+ * d(weight*loss)/d pred (zeros for ignored rows); n_word is counted on the device (no host sync). */
+int ctcb200_ce_workspace_bytes(int64_t rows, size_t *out_bytes);
+int ctcb200_ce_loss_grad(const float *pred, const int64_t *gold, int64_t rows, int V, int ignore_index,
+                         float smoothing, float weight, float *loss_out, float *grad, void *workspace,
+                         size_t workspace_bytes, ctcb200_stream_t stream);
+
 /* Debug: copies the device status word to *host_status (synchronises `stream`). */
 int ctcb200_read_status(const void *workspace, int *host_status, ctcb200_stream_t stream);
 

@@ -153,3 +153,33 @@ def test_no_out_of_bounds_writes_guard_zones():
             _, rg = ref_ctc(c["logits"], c["targets"], c["input_lengths"], c["target_lengths"], reduction="mean",
                             zero_infinity=True)
             assert (grad.cpu() - rg).abs().max().item() <= 1e-4, mode
+
+
+@pytest.mark.parametrize("eps", [0.0, 0.1])
+def test_attention_ce_matches_reference_formulation(eps):
+    """the attention-branch loss on the sweep kernels vs the reference's cal_loss
+    (Predictor/Utils/loss.py:26-51) restated with torch ops on the CPU."""
+    from asr_chinese_e2e_b200 import attention_ce_b200
+    g = torch.Generator().manual_seed(7)
+    for (N, Ln, C) in ((3, 7, 37), (5, 11, 4234), (2, 5, 130)):
+        pred = torch.randn(N, Ln, C, generator=g) * 2.0
+        gold = torch.randint(1, C, (N, Ln), generator=g)
+        gold[0, -2:] = 0; gold[-1, 1] = 0                          # PAD rows are ignored
+        w = 0.7
+        x = pred.clone().requires_grad_(True)
+        p2, g2 = x.view(-1, C), gold.view(-1)
+        if eps > 0:
+            one_hot = torch.zeros_like(p2).scatter(1, g2.view(-1, 1), 1)
+            one_hot = one_hot * (1 - eps) + (1 - one_hot) * eps / C
+            ref = -(one_hot * F.log_softmax(p2, 1)).sum(1).masked_select(g2.ne(0)).sum() / g2.ne(0).sum()
+        else:
+            ref = F.cross_entropy(p2, g2, ignore_index=0, reduction="mean")
+        (w * ref * 1.5).backward()
+        xc = pred.cuda().requires_grad_(True)
+        got = attention_ce_b200(xc, gold.cuda(), smoothing=eps, weight=w)
+        (got * 1.5).backward()                                     # upstream gradient != 1: rescale path
+        assert abs(got.item() - w * ref.item()) <= 1e-5 * abs(ref.item()), (N, Ln, C)
+        assert (xc.grad.cpu() - x.grad).abs().max().item() <= 1e-6, (N, Ln, C)
+        assert torch.all(xc.grad.view(-1, C)[g2.eq(0).cuda()] == 0)
+        with torch.no_grad():
+            assert abs(attention_ce_b200(pred.cuda(), gold.cuda(), eps).item() - ref.item()) <= 1e-5 * abs(ref.item())
