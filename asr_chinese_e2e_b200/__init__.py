@@ -6,9 +6,9 @@ Importing the package does not load the CUDA library; the first call does, and r
 libctcb200.so is missing -- there is no CPU fallback.
 """
 from .ce import attention_ce_b200  # noqa: F401
-from .ctc import CTCLossB200, ctc_loss_b200  # noqa: F401
+from .ctc import CTCLossB200, ctc_greedy_cer_b200, ctc_loss_b200  # noqa: F401
 from .joint import JointCTCAttention, Pack  # noqa: F401
 from .sharded import combine_equal_shards, combine_sharded_mean, sharded_ctc_loss  # noqa: F401
 
-__all__ = ["CTCLossB200", "ctc_loss_b200", "attention_ce_b200", "JointCTCAttention", "Pack", "combine_equal_shards", "combine_sharded_mean",
+__all__ = ["CTCLossB200", "ctc_loss_b200", "attention_ce_b200", "ctc_greedy_cer_b200", "JointCTCAttention", "Pack", "combine_equal_shards", "combine_sharded_mean",
            "sharded_ctc_loss"]

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(_HERE, "libctcb200.so")
 SOURCES = ["ctcb200.cu"]
-HEADERS = ["ptx.cuh", "layout.h", "stream_kernels.cuh", "lattice_kernel.cuh", "ce_kernel.cuh",
+HEADERS = ["ptx.cuh", "layout.h", "stream_kernels.cuh", "lattice_kernel.cuh", "ce_kernel.cuh", "decode_kernel.cuh",
            os.path.join("..", "..", "include", "ctcb200.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -58,6 +58,7 @@ SIGNATURES = {
     "ctcb200_loss_grad_stages": (_i, [_i, _p, _p, _i64, _i64, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _sz, _p]),
     "ctcb200_backward": (_i, [_p, _p, _i64, _i64, _p, _i64, _i, _f, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "ctcb200_rescale_grad": (_i, [_p, _p, _i64, _p, _p, _i, _i, _i, _p]),
+    "ctcb200_greedy_decode": (_i, [_p, _i64, _i64, _i, _i, _i, _i, _i, _p, _sz, _p, _p, _p, _p]),
     "ctcb200_ce_workspace_bytes": (_i, [_i64, ctypes.POINTER(_sz)]),
     "ctcb200_ce_loss_grad": (_i, [_p, _p, _i64, _i, _i, _f, _f, _p, _p, _p, _sz, _p]),
     "ctcb200_read_status": (_i, [_p, ctypes.POINTER(_i), _p]),

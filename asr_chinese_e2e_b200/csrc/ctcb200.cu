@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include "ce_kernel.cuh"
+#include "decode_kernel.cuh"
 #include "lattice_kernel.cuh"
 #include "layout.h"
 #include "stream_kernels.cuh"
@@ -86,6 +87,7 @@ struct K1Args {
     const float *logits; const int64_t *targets; int64_t tnumel; const int *Tb, *Ub; const int64_t *toff;
     const int *rowstart; float *lp_lab; int *hdr; int B, T, V, Lp, blank;
     float *grad; int reduction; float inv_batch;   // fused (2-sweep) mode only
+    int *best;
 };
 struct K3Args {
     const float *logits; const int64_t *targets; int64_t tnumel; const int *Tb, *Ub; const int64_t *toff;
@@ -100,7 +102,7 @@ cudaError_t launch_k1x(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
     if (e != cudaSuccess) return e;
     k1_lse_gather<NT, MAXC, EXACT, FUSED><<<c.grid, NT, c.smem, s>>>(
         a.logits, a.targets, a.tnumel, a.Tb, a.Ub, a.toff, a.rowstart, a.lp_lab, a.hdr, a.B, a.T, a.V, a.Lp,
-        a.blank, c.nst, c.slot_bytes, a.grad, a.reduction, a.inv_batch);
+        a.blank, c.nst, c.slot_bytes, a.grad, a.reduction, a.inv_batch, a.best);
     return cudaGetLastError();
 }
 template <int NT, int MAXC, bool EXACT>
@@ -192,6 +194,8 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
 
     const bool fused = fg != nullptr;
     const int stages = fused ? fg->stages : 7;
+    const bool want_argmax = (zero_infinity & CTCB200_FLAG_DECODE) != 0;
+    zero_infinity &= 1;
     cudaError_t e = cudaSuccess;
     if (stages & 1) {
     prefer_max_carveout(k0_prep);
@@ -204,14 +208,15 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     bool exact1;
     stream_pick(V, env_int(fused ? "CTCB200_K1F_NT" : "CTCB200_K1_NT", fused ? 128 : 64), &nt1, &rounds1, &exact1);
     if (fused)
-        rc = stream_cfg(V, 0, 64 + (size_t)g.Lp * 4, dev.sms, 4, 2, "CTCB200_K1F_NST", "CTCB200_K1F_CPS", &c);
+        rc = stream_cfg(V, 0, 96 + (size_t)g.Lp * 4, dev.sms, 4, 2, "CTCB200_K1F_NST", "CTCB200_K1F_CPS", &c);
     else
-        rc = stream_cfg(V, 0, 64 + (size_t)g.Lp * 4, dev.sms, nt1 == 64 ? 2 : 3, nt1 == 64 ? 5 : 3,
+        rc = stream_cfg(V, 0, 96 + (size_t)g.Lp * 4, dev.sms, nt1 == 64 ? 2 : 3, nt1 == 64 ? 5 : 3,
                         "CTCB200_K1_NST", "CTCB200_K1_CPS", &c);
     if (rc) return rc;
     {
         const K1Args a = {logits, targets, tnumel, Tb, Ub, toff, rowstart, lp_lab, hdr, B, T, V, g.Lp, blank,
-                          fused ? fg->grad : nullptr, fused ? fg->reduction : 0, fused ? fg->inv_batch : 0.f};
+                          fused ? fg->grad : nullptr, fused ? fg->reduction : 0, fused ? fg->inv_batch : 0.f,
+                          want_argmax ? (int *)(ws + w.best) : nullptr};
         if (fused) {
             if (nt1 == 64) e = STREAM_DISPATCH(launch_k1f, 64, rounds1, exact1, c, s, a);
             else e = STREAM_DISPATCH(launch_k1f, 128, rounds1, exact1, c, s, a);
@@ -359,6 +364,7 @@ int ctcb200_backward(const float *logits, const int64_t *targets, int64_t target
     if (rc) return rc;
     if (!grad_out || !grad_logits) return CTCB200_ERR_NULL;
     if ((uintptr_t)grad_logits & 15) return CTCB200_ERR_ALIGN;
+    zero_infinity &= 1;
     if (reduction < 0 || reduction > 2) return CTCB200_ERR_REDUCTION;
     if (targets_stride < 0 || targets_numel < 0 || grad_out_stride < 0) return CTCB200_ERR_SHAPE;
     if (B == 0) return CTCB200_OK;
@@ -404,6 +410,43 @@ int ctcb200_rescale_grad(float *grad_logits, const float *grad_out, int64_t grad
     k4_rescale<<<dim3(per, B), 256, 0, (cudaStream_t)stream>>>(grad_logits, grad_out, grad_out_stride, applied_in,
                                                                  applied_out, T, V);
     return (int)cudaGetLastError();
+}
+
+// ---- greedy CTC decode + edit distance --------------------------------------------
+int ctcb200_greedy_decode(const int64_t *targets, int64_t targets_stride, int64_t targets_numel, int B, int T, int V,
+                          int Umax, int blank, const void *workspace, size_t workspace_bytes, int *edit_out,
+                          int *hyp_len_out, int64_t *hyp_out, ctcb200_stream_t stream) {
+    Geom g;
+    Workspace w;
+    int rc = check_common(workspace, targets, workspace, workspace, B, T, V, Umax, blank, workspace, workspace_bytes,
+                          &g, &w);
+    if (rc == CTCB200_ERR_ALIGN && !((uintptr_t)workspace & 255)) rc = 0;
+    if (rc) return rc;
+    if (!edit_out || !hyp_len_out) return CTCB200_ERR_NULL;
+    if (B == 0) return CTCB200_OK;
+    const unsigned char *ws = (const unsigned char *)workspace;
+    const int *Tb = (const int *)(ws + w.Tb), *Ub = (const int *)(ws + w.Ub), *best = (const int *)(ws + w.best);
+    const int64_t *toff = (const int64_t *)(ws + w.toff);
+    const int64_t tnumel = targets_stride ? (int64_t)B * targets_stride : targets_numel;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t smem = 4 * (size_t)T * sizeof(int);
+    if (smem > kSmemBudget) return CTCB200_ERR_SHAPE;
+    const int grid = (B + 3) / 4;
+    cudaError_t e;
+#define K5(N)                                                                                                   \
+    do {                                                                                                        \
+        e = cudaFuncSetAttribute(k5_greedy_cer<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        if (e == cudaSuccess) {                                                                                 \
+            k5_greedy_cer<N><<<grid, 128, smem, s>>>(targets, tnumel, Tb, Ub, toff, best, edit_out, hyp_len_out, \
+                                                     hyp_out, B, T, V, blank);                                  \
+            e = cudaGetLastError();                                                                             \
+        }                                                                                                       \
+    } while (0)
+    if (Umax <= 64) K5(2);
+    else if (Umax <= 128) K5(4);
+    else K5(8);
+#undef K5
+    return (int)e;
 }
 
 // ---- attention-branch cross-entropy -------------------------------------------

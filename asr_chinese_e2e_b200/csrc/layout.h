@@ -44,6 +44,7 @@ struct Workspace {
     size_t lp_lab;    // float[B*T*Lp]
     size_t gam;       // float[B*T*Lp]
     size_t ab;        // float[B*T*Sp]
+    size_t best;      // int[B*T]   per-frame argmax class (greedy CTC path), written by the sweep
     size_t total;
 };
 
@@ -60,6 +61,7 @@ static inline Workspace workspace_layout(int B, int T, const Geom &g) {
     w.lp_lab = o;    o += align_up(sizeof(float) * b * T * g.Lp);
     w.gam = o;       o += align_up(sizeof(float) * b * T * g.Lp);
     w.ab = o;        o += align_up(sizeof(float) * b * T * g.Sp);
+    w.best = o;      o += align_up(sizeof(int) * b * T);
     w.total = o;
     return w;
 }

@@ -194,7 +194,8 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
               const int *__restrict__ Tb_arr, const int *__restrict__ Ub_arr,
               const int64_t *__restrict__ toff_arr, const int *__restrict__ rowstart,
               float *__restrict__ lp_lab, int *__restrict__ hdr, int B, int T, int V, int Lp, int blank,
-              int nst, uint32_t slot_bytes, float *__restrict__ grad, int reduction, float inv_batch) {
+              int nst, uint32_t slot_bytes, float *__restrict__ grad, int reduction, float inv_batch,
+              int *__restrict__ best) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int r0, nrows;
@@ -203,8 +204,8 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
     if (nrows <= 0) return;
 
     uint64_t *bars = (uint64_t *)(smem + (size_t)nst * slot_bytes);
-    float *red = (float *)(bars + nst);              // [2 parity][2 max/sum][4 warps]
-    int *cls_s = (int *)(red + 16);                  // [Lp] class id per frame slot
+    float *red = (float *)(bars + nst);              // [2 parity][3 max/sum/argmax][4 warps]
+    int *cls_s = (int *)(red + 24);                  // [Lp] class id per frame slot
     const uint32_t slot0 = smem_u32(smem), bar0 = smem_u32(bars);
     if (tid == 0) {
         for (int s = 0; s < nst; ++s) mbar_init(bar0 + 8 * s, 1);
@@ -298,7 +299,7 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
             cg[kk] = -1; xg[kk] = 0.f;
             if (k < Lp) { cg[kk] = cls_s[k]; if (cg[kk] >= 0) xg[kk] = srow[cg[kk]]; }
         }
-        float *rd = red + (i & 1) * 8;
+        float *rd = red + (i & 1) * 12;
         mx = warp_max(mx);
         if (lane == 0) rd[warp] = mx;
         __syncthreads();                                   // B1: slot fully consumed
@@ -310,6 +311,27 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
         }
         const float m = NT == 128 ? fmaxf(fmaxf(rd[0], rd[1]), fmaxf(rd[2], rd[3])) : fmaxf(rd[0], rd[1]);
         const float m2 = m * kLog2e;
+        if (best != nullptr) {   // per-frame argmax (greedy CTC decode): lowest class index attaining the row maximum
+            int cand = 0x7fffffff;
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k) {
+                const int e = 4 * (1 + tid + k * NT) - head;
+                if (v[k].w == m) cand = min(cand, e + 3);
+                if (v[k].z == m) cand = min(cand, e + 2);
+                if (v[k].y == m) cand = min(cand, e + 1);
+                if (v[k].x == m) cand = min(cand, e);
+            }
+            if (tid == 0 || (tid == 1 && nch > 1)) {
+                const int e = 4 * (tid == 0 ? 0 : nch - 1) - head;
+                if (ve.w == m) cand = min(cand, e + 3);
+                if (ve.z == m) cand = min(cand, e + 2);
+                if (ve.y == m) cand = min(cand, e + 1);
+                if (ve.x == m) cand = min(cand, e);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+            if (lane == 0) ((int *)rd)[8 + warp] = cand;
+        }
         float sum = 0.f;
 #pragma unroll
         for (int k = 0; k < MAXC; ++k) {
@@ -327,6 +349,10 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
         __syncthreads();                                   // B2
         const float tot = NT == 128 ? (rd[4] + rd[5]) + (rd[6] + rd[7]) : rd[4] + rd[5];
         const float lse2 = m2 + lg2f(tot);
+        if (best != nullptr && tid == 0) {
+            const int *ri = (const int *)rd + 8;
+            best[(size_t)cc.b * T + cc.t] = NT == 128 ? min(min(ri[0], ri[1]), min(ri[2], ri[3])) : min(ri[0], ri[1]);
+        }
         float *frame = lp_lab + ((size_t)cc.b * T + cc.t) * Lp;
 #pragma unroll
         for (int kk = 0; kk < MAXG; ++kk) {

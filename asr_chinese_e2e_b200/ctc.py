@@ -107,7 +107,22 @@ def _n_chunks(B, requested):
     return max(1, min(int(n), B)) if B else 1
 
 
-def _two_sweep_pipeline(ctx, L, x, tg, stride, il, tl, B, T, V, umax, blank, zi, red, inv_b, nll, grad, reduction):
+def _decode_chunks(L, decode, tg, stride, chunks, T, V, umax, blank, stream, dev, B):
+    """Greedy CTC decode + edit distance from the argmax the sweep left in each chunk's workspace.
+    chunks: list of (lo, n, ws_ptr, ws_bytes).  Fills the caller's `decode` dict with device tensors."""
+    edit = torch.empty(B, dtype=torch.int32, device=dev)
+    hlen = torch.empty(B, dtype=torch.int32, device=dev)
+    hyp = torch.empty(B, T, dtype=torch.int64, device=dev) if decode.get("want_hyp", True) else None
+    for lo, n, wsp, wsb in chunks:
+        _lib.check(L.ctcb200_greedy_decode(tg.data_ptr() + lo * stride * 8, stride, tg.numel() - lo * stride, n, T, V, umax,
+                                           blank, wsp, wsb, edit.data_ptr() + lo * 4, hlen.data_ptr() + lo * 4,
+                                           hyp.data_ptr() + lo * T * 8 if hyp is not None else None, stream.cuda_stream),
+                   "ctcb200_greedy_decode")
+    decode.update(edit_distance=edit, hyp_len=hlen, hyp=hyp)
+
+
+def _two_sweep_pipeline(ctx, L, x, tg, stride, il, tl, B, T, V, umax, blank, zi, red, inv_b, nll, grad, reduction,
+                        decode=None):
     """Default training path.  Two utterance chunks (80 % / 20 %):
 
         main stream:  sweep(a)  sweep(b)            patch(a)   patch(b)
@@ -155,6 +170,9 @@ def _two_sweep_pipeline(ctx, L, x, tg, stride, il, tl, B, T, V, umax, blank, zi,
         if _DEBUG:
             for c in range(n_ch):
                 _check_status(ws[ws_off[c]:], main.cuda_stream)
+        if decode is not None:
+            _decode_chunks(L, decode, tg, stride, [(bounds[c], bounds[c + 1] - bounds[c], ws.data_ptr() + ws_off[c],
+                                                    ws_bytes[c]) for c in range(n_ch)], T, V, umax, blank, main, dev, B)
     ctx.cfg = (stride, B, T, V, umax, blank, zi, red, 0, 0, n_ch, inv_b, True)
     ctx.applied = torch.ones(B, dtype=torch.float32, device=dev)
     ctx.save_for_backward(grad)
@@ -173,7 +191,7 @@ class _CTCLossB200Fn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, logits, targets, input_lengths, target_lengths, blank, reduction, zero_infinity,
-                inv_batch, max_target_length, fused, chunks):
+                inv_batch, max_target_length, fused, chunks, decode):
         x, tg, stride, il, tl, B, T, V, umax = _prepare(logits, targets, input_lengths, target_lengths,
                                                         blank, max_target_length)
         L = _lib.lib()
@@ -181,14 +199,14 @@ class _CTCLossB200Fn(torch.autograd.Function):
         fused = bool(need_grad and fused)
         two_sweep = bool(int(os.environ.get("CTCB200_TWO_SWEEP", "1")))
         red = _RED[reduction]
-        zi = int(bool(zero_infinity))
+        zi = int(bool(zero_infinity)) | (2 if decode is not None else 0)   # bit 1: record per-frame argmax
         inv_b = float(inv_batch) if inv_batch is not None else (1.0 / max(B, 1))
         dev = x.device
         nll = torch.empty(B, dtype=torch.float32, device=dev)
         grad = torch.empty_like(x) if fused else None
         if fused and two_sweep and chunks is None and "CTCB200_CHUNKS" not in os.environ:
             out = _two_sweep_pipeline(ctx, L, x, tg, stride, il, tl, B, T, V, umax, int(blank), zi, red, inv_b,
-                                      nll, grad, reduction)
+                                      nll, grad, reduction, decode)
             return out
         n_ch = _n_chunks(B, chunks)
         per = (B + n_ch - 1) // n_ch if B else 0
@@ -250,6 +268,10 @@ class _CTCLossB200Fn(torch.autograd.Function):
             if _DEBUG:
                 for c in range(n_ch):
                     _check_status(ws[c * ws_bytes:], main.cuda_stream)
+            if decode is not None:
+                _decode_chunks(L, decode, tg, stride,
+                               [(c * per, min((c + 1) * per, B) - c * per, ws.data_ptr() + c * ws_bytes, ws_bytes)
+                                for c in range(n_ch) if c * per < B], T, V, umax, int(blank), main, dev, B)
         ctx.cfg = (stride, B, T, V, umax, int(blank), zi, red, ws_bytes, per, n_ch, inv_b, fused)
         if need_grad:
             if fused:
@@ -278,7 +300,7 @@ class _CTCLossB200Fn(torch.autograd.Function):
                                                   ctx.applied.data_ptr(), applied_new.data_ptr(), B, T, V, stream),
                            "ctcb200_rescale_grad")
                 ctx.applied = applied_new
-            return (grad,) + (None,) * 10
+            return (grad,) + (None,) * 11
         x, tg, ws = ctx.saved_tensors
         grad = torch.empty_like(x)
         xs = x.element_size() * T * V
@@ -295,12 +317,12 @@ class _CTCLossB200Fn(torch.autograd.Function):
                                               go.data_ptr() + lo * gs, 1 if red == 0 else 0, red, inv_b, n, T, V,
                                               umax, blank, zi, grad.data_ptr() + lo * xs,
                                               ws.data_ptr() + c * ws_bytes, ws_bytes, stream), "ctcb200_backward")
-        return (grad,) + (None,) * 10
+        return (grad,) + (None,) * 11
 
 
 def ctc_loss_b200(logits, targets, input_lengths, target_lengths, blank: int = 0,
                   reduction: str = "mean", zero_infinity: bool = False, *, inv_batch=None,
-                  max_target_length=None, fused=None, chunks=None):
+                  max_target_length=None, fused=None, chunks=None, decode=None):
     """CTC loss on batch-major logits; same flags and results as ``F.ctc_loss`` (see module doc).
 
     inv_batch: 1/(global batch) for 'mean' when the batch is sharded over ranks (default 1/B).
@@ -311,6 +333,9 @@ def ctc_loss_b200(logits, targets, input_lengths, target_lengths, blank: int = 0
         is the default when the logits require grad (env CTCB200_FUSED=0 to disable); costs one
         extra [B,T,V] buffer held until backward, like autograd's own saved log-probs would.
     chunks: utterance chunks of the two-stream pipeline (default env CTCB200_CHUNKS or 1).
+    decode: optional dict; if given it is filled with the on-device greedy (best-path) decode of the same
+        forward pass -- ``edit_distance`` int32[B] (token-level Levenshtein distance to the targets),
+        ``hyp_len`` int32[B], ``hyp`` int64[B,T] (blank-padded; skip with ``decode={"want_hyp": False}``).
     """
     if reduction not in _RED:
         raise ValueError(f"reduction must be one of {list(_RED)}")
@@ -319,7 +344,19 @@ def ctc_loss_b200(logits, targets, input_lengths, target_lengths, blank: int = 0
     if torch.is_tensor(targets) and targets.dim() == 1:
         chunks = 1
     return _CTCLossB200Fn.apply(logits, targets, input_lengths, target_lengths, blank, reduction,
-                                zero_infinity, inv_batch, max_target_length, fused, chunks)
+                                zero_infinity, inv_batch, max_target_length, fused, chunks, decode)
+
+
+def ctc_greedy_cer_b200(logits, targets, input_lengths, target_lengths, blank: int = 0):
+    """Best-path CTC decode and character error rate, all on the device (one read sweep of the logits).
+    Returns (cer_percent 0-dim tensor = 100 * mean_b(edit_b / max(U_b,1)), info dict as in ``decode``)."""
+    info = {}
+    with torch.no_grad():
+        ctc_loss_b200(logits, targets, input_lengths, target_lengths, blank=blank, reduction="none",
+                      zero_infinity=True, decode=info)
+    tl = torch.as_tensor(target_lengths).to(info["edit_distance"].device)
+    cer = (info["edit_distance"].float() / tl.clamp(min=1).float()).mean() * 100.0
+    return cer, info
 
 
 class CTCLossB200(torch.nn.Module):

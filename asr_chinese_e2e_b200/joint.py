@@ -109,11 +109,12 @@ class JointCTCAttention:
     ctc_zero_infinity: bool = True
 
     def init_ctc(self, d_model: int, vocab_size: int, ctc_weight: float = 0.3, ctc_zero_infinity: bool = True,
-                 smoothing: float = 0.0):
+                 smoothing: float = 0.0, ctc_cer_on_device: bool = False):
         self.ctc_head = torch.nn.Linear(d_model, vocab_size)
         self.ctc_weight = float(ctc_weight)
         self.ctc_zero_infinity = bool(ctc_zero_infinity)
         self.att_smoothing = float(smoothing)
+        self.ctc_cer_on_device = bool(ctc_cer_on_device)   # adds a `ctc_cer` metric (greedy CTC, device-side)
 
     # -- forward: encoder tap + CTC head, then the decoder exactly as the reference calls it --------
     def forward(self, input):
@@ -135,9 +136,11 @@ class JointCTCAttention:
         # ctc_weight is folded into the op's normaliser (inv_batch = w/B): the op returns w*ctc and its
         # speculative gradient is already the final one, so backward() costs one empty launch instead of a
         # rescaling sweep over [B,T,V]
+        dec = {"want_hyp": False} if (getattr(self, "ctc_cer_on_device", False) and output.ctc_logits.is_cuda) else None
         wctc = ctc_loss_b200(output.ctc_logits.float(), input.tgt_for_input, input.wave_len, input.tgt_len,
                              blank=IGNORE_ID, reduction="mean", zero_infinity=self.ctc_zero_infinity,
-                             inv_batch=(w if w > 0 else 1.0) / max(B, 1))
+                             inv_batch=(w if w > 0 else 1.0) / max(B, 1), decode=dec)
+        self._last_decode = dec
         if w > 0:
             return wctc + (1.0 - w) * att, wctc / w, att
         return att + 0.0 * wctc, wctc, att
@@ -151,7 +154,12 @@ class JointCTCAttention:
             g = [t for t in g if t != IGNORE_ID]
             cer += edit_distance(h[: len(g)], g) / max(len(g), 1)
         cer = cer * 100.0 / max(hyp.size(0), 1)
-        return Pack(loss=loss, cer=torch.tensor([cer]), ctc_loss=ctc.detach(), att_loss=att.detach())
+        pack = Pack(loss=loss, cer=torch.tensor([cer]), ctc_loss=ctc.detach(), att_loss=att.detach())
+        dec = getattr(self, "_last_decode", None)
+        if dec:   # CTC-branch CER of the same forward pass, computed entirely on the device (no sync here)
+            tl = input.tgt_len.to(dec["edit_distance"].device).clamp(min=1).float()
+            pack.add(ctc_cer=((dec["edit_distance"].float() / tl).mean() * 100.0).reshape(1))
+        return pack
 
     def iterate(self, input, optimizer=None, is_train=True):
         output = self.forward(input)

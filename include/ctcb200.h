@@ -64,6 +64,10 @@ enum ctcb200_error {
 
 enum ctcb200_reduction { CTCB200_REDUCE_NONE = 0, CTCB200_REDUCE_MEAN = 1, CTCB200_REDUCE_SUM = 2 };
 
+/* The `zero_infinity` argument of the forward-type calls is a small bit field: bit 0 = zero_infinity,
+ * bit 1 = also record the per-frame argmax class for ctcb200_greedy_decode (costs ~5 % of the sweep). */
+enum ctcb200_forward_flags { CTCB200_FLAG_ZERO_INFINITY = 1, CTCB200_FLAG_DECODE = 2 };
+
 /* bits of the device status word */
 enum ctcb200_status_bits {
     CTCB200_ST_BAD_INPUT_LENGTH = 1,  /* in_len[b] outside [0,T]: clamped */
@@ -148,6 +152,18 @@ int ctcb200_loss_grad_stages(int stages, const float *logits, const int64_t *tar
 int ctcb200_rescale_grad(float *grad_logits, const float *grad_out, int64_t grad_out_stride,
                          const float *applied_in, float *applied_out, int B, int T, int V,
                          ctcb200_stream_t stream);
+
+/* On-device greedy (best-path) CTC decode + token-level edit distance: replaces the
+ * per-step D->H sync and Python Levenshtein loop of cal_metrics (transformer_official.py:87-91,
+ * Predictor/Utils/score.py:4-13) for a CTC-branch character error rate.  Uses the per-frame argmax the
+ * sweep of ctcb200_forward / _loss_only / _loss_grad left in `workspace` (call them with
+ * zero_infinity | CTCB200_FLAG_DECODE).  edit_out[B]: Levenshtein
+ * distance between the collapsed best path and the labels; hyp_len_out[B]; hyp_out (optional)
+ * int64 [B,T], padded with blank. */
+int ctcb200_greedy_decode(const int64_t *targets, int64_t targets_stride, int64_t targets_numel,
+                          int B, int T, int V, int Umax, int blank, const void *workspace,
+                          size_t workspace_bytes, int *edit_out, int *hyp_len_out, int64_t *hyp_out,
+                          ctcb200_stream_t stream);
 
 /* Attention-branch loss on the same sweep machinery: cross-entropy with optional label
  * smoothing over pred[rows, V] logits, rows whose gold == ignore_index skipped -- the reference's

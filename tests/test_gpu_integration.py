@@ -183,3 +183,31 @@ def test_attention_ce_matches_reference_formulation(eps):
         assert torch.all(xc.grad.view(-1, C)[g2.eq(0).cuda()] == 0)
         with torch.no_grad():
             assert abs(attention_ce_b200(pred.cuda(), gold.cuda(), eps).item() - ref.item()) <= 1e-5 * abs(ref.item())
+
+
+def test_greedy_decode_and_edit_distance_on_device():
+    """best-path decode + Levenshtein on the device vs the host implementation."""
+    from asr_chinese_e2e_b200 import ctc_greedy_cer_b200, ctc_loss_b200
+    from asr_chinese_e2e_b200.joint import edit_distance, greedy_ctc_ids
+    for (B, T, V, U, dist) in ((7, 61, 53, 13, "D2"), (5, 200, 4234, 30, "D2"), (4, 300, 97, 100, "D1"), (3, 90, 31, 150, "D1")):
+        c = make_case(B, T, V, U, 77, dist=dist)
+        c["target_lengths"][0] = 0
+        x = c["logits"].cuda()
+        cer, info = ctc_greedy_cer_b200(x, c["targets"].cuda(), c["input_lengths"].cuda(), c["target_lengths"].cuda())
+        want_h = greedy_ctc_ids(c["logits"], c["input_lengths"])
+        tot = 0.0
+        for b in range(B):
+            n = int(info["hyp_len"][b])
+            assert info["hyp"][b, :n].tolist() == want_h[b], (B, T, V, U, b)
+            assert torch.all(info["hyp"][b, n:] == 0)
+            ref = c["targets"][b, : int(c["target_lengths"][b])].tolist()
+            d = edit_distance(want_h[b], ref)
+            assert int(info["edit_distance"][b]) == d, (B, T, V, U, b)
+            tot += d / max(len(ref), 1)
+        assert abs(cer.item() - 100.0 * tot / B) < 1e-3
+    # the training forward fills the same dict as a by-product (no extra sweep)
+    info2 = {}
+    xg = c["logits"].cuda().requires_grad_(True)
+    ctc_loss_b200(xg, c["targets"].cuda(), c["input_lengths"].cuda(), c["target_lengths"].cuda(), zero_infinity=True,
+                  decode=info2).backward()
+    assert torch.equal(info2["edit_distance"], info["edit_distance"]) and torch.equal(info2["hyp"], info["hyp"])
