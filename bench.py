@@ -295,6 +295,7 @@ def main():
             line["e2e"] = run_e2e(torch, c, args, dev)
             # the training-shaped variant: the gradient's consumer is the next GPU kernel, only the loss goes back
             line["e2e_grad_on_device"] = run_e2e(torch, c, args, dev, grad_to_host=False)
+        line["torch_cuda_baseline"] = run_torch_cuda(torch, x, tg, il, tl)
         if not args.no_cpu:
             cb = cpu_reference_line(args, c, steps=5, warmup=2)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -312,6 +313,30 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_torch_cuda(torch, x, tg, il, tl):
+    """Secondary GPU baseline: torch's own CUDA log_softmax + ctc_loss + backward on the same
+    B200 and inputs -- what the reference as written would execute once a CTC call were added."""
+    import torch.nn.functional as F
+
+    def step():
+        x.grad = None
+        F.ctc_loss(F.log_softmax(x, -1).transpose(0, 1), tg, il, tl, blank=0, reduction="mean",
+                   zero_infinity=False).backward()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    x.grad = None
+    ms = e0.elapsed_time(e1) / 10
+    return {"value": B_ / (ms / 1e3), "unit": UNIT, "ms_per_step": ms,
+            "what": f"torch {torch.__version__} CUDA F.log_softmax + F.ctc_loss(mean) + backward, same inputs, 10 steps"}
 
 
 def run_e2e(torch, c, args, dev, grad_to_host=True):
