@@ -27,6 +27,7 @@
 #pragma once
 #include "layout.h"
 #include "ptx.cuh"
+#include "stream_kernels.cuh"
 
 namespace ctcb200 {
 
@@ -375,9 +376,17 @@ k2_lattice(const int64_t *__restrict__ targets, int64_t tnumel, const int *__res
            const int *__restrict__ Ub_arr, const int64_t *__restrict__ toff_arr, int *__restrict__ flags,
            const float *__restrict__ lp_lab, float *__restrict__ gam, float *__restrict__ ab_ws,
            float *__restrict__ nll, float *__restrict__ loss_sums, unsigned *__restrict__ ticket, int B,
-           int T, int zero_inf) {
+           int T, int zero_inf, float *__restrict__ zero_grad, const int *__restrict__ rowstart, int V) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_lat = (B + 1) / 2;
+    if ((int)blockIdx.x >= n_lat) {
+        // Extra CTAs of the same launch: while the (latency-bound) lattice CTAs run, these write the zeros of
+        // the padded frames of grad -- HBM work of the step that would otherwise sit in the sweep kernel.
+        zero_padded_frames<128>(zero_grad, Tb_arr, rowstart, B, T, V, tid, (int)blockIdx.x - n_lat,
+                                (int)gridDim.x - n_lat);
+        return;
+    }
     const int pair = warp >> 1, dir = warp & 1;
     const int b = 2 * blockIdx.x + pair;
     if (b >= B) return;                                          // odd batch: the last CTA has one utterance

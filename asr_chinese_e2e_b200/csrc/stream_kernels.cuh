@@ -102,6 +102,11 @@ __device__ __forceinline__ void cursor_next(RowCursor &c, const int *__restrict_
 
 // Balanced split of n items over the grid with 32-bit arithmetic only (a 64-bit division would be a
 // CALL to a software routine and force spills of everything live across it).
+__device__ __forceinline__ void worker_share(int n, int bid, int G, int &first, int &count) {
+    const int base = n / G, rem = n - base * G;
+    first = bid * base + (bid < rem ? bid : rem);
+    count = base + (bid < rem ? 1 : 0);
+}
 __device__ __forceinline__ void grid_share(int n, int &first, int &count) {
     const int G = (int)gridDim.x, bid = (int)blockIdx.x;
     const int base = n / G, rem = n - base * G;
@@ -152,11 +157,12 @@ __device__ __forceinline__ void fill_span(float *p, size_t n, int tid, float val
 // Zero the padded frames (t >= T_b) of the whole batch: every CTA takes an equal share of them.
 template <int NT>
 __device__ __forceinline__ void zero_padded_frames(float *__restrict__ grad, const int *__restrict__ Tb_arr,
-                                                   const int *__restrict__ rowstart, int B, int T, int V, int tid) {
+                                                   const int *__restrict__ rowstart, int B, int T, int V, int tid,
+                                                   int worker = -1, int nworkers = 0) {
     const int Zn = B * T - rowstart[B];
     if (Zn <= 0) return;
     int z0, zc;
-    grid_share(Zn, z0, zc);
+    if (worker < 0) grid_share(Zn, z0, zc); else worker_share(Zn, worker, nworkers, z0, zc);
     if (zc <= 0) return;
     long long z = z0;
     const long long z1 = (long long)z0 + zc;
@@ -195,12 +201,12 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
               const int64_t *__restrict__ toff_arr, const int *__restrict__ rowstart,
               float *__restrict__ lp_lab, int *__restrict__ hdr, int B, int T, int V, int Lp, int blank,
               int nst, uint32_t slot_bytes, float *__restrict__ grad, int reduction, float inv_batch,
-              int *__restrict__ best) {
+              int *__restrict__ best, int zero_pad_here) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int r0, nrows;
     grid_share(rowstart[B], r0, nrows);
-    if (FUSED) zero_padded_frames<NT>(grad, Tb_arr, rowstart, B, T, V, tid);
+    if (FUSED && zero_pad_here) zero_padded_frames<NT>(grad, Tb_arr, rowstart, B, T, V, tid);
     if (nrows <= 0) return;
 
     uint64_t *bars = (uint64_t *)(smem + (size_t)nst * slot_bytes);

@@ -95,12 +95,13 @@ def make_case(B, T, V, Umax, seed, dist="D1", full_lengths=False, full_targets=F
     il = torch.maximum(il, torch.minimum(tl + rep, torch.tensor(T)))
     k = 1
     for _ in range(n_infeasible):            # truly infeasible: in_len = U + rep - 1
-        il[k] = max(int(tl[k] + rep[k]) - 1, 1)
+        il[k] = min(max(int(tl[k] + rep[k]) - 1, 1), T)
         k += 1
     for _ in range(n_partial):               # partial lattice band: U+rep <= in_len < 2U+1
         lo, hi = int(tl[k] + rep[k]), int(2 * tl[k])
         il[k] = min(max(lo, (lo + hi) // 2), T)
         k += 1
+    il = il.clamp(max=T)
     logits = make_logits(B, T, V, gen, dist, targets, tl, il)
     return dict(logits=logits, targets=targets, input_lengths=il, target_lengths=tl)
 

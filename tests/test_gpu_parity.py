@@ -136,6 +136,34 @@ def test_c4_like_long_with_infeasible():
         assert torch.all(g[b] == 0)
 
 
+def test_c4_full_size_properties():
+    """BASELINE config 4 at full size (B=64, T=1500, V=4234, U<=120, zero_infinity=True, 8 infeasible + 8
+    partial-lattice utterances): size-independent properties + a float64 spot check."""
+    c = make_config("C4", dist="D1")
+    B, T, V = c["logits"].shape
+    op = _op()
+    x = c["logits"].cuda().requires_grad_(True)
+    tg, il, tl = c["targets"].cuda(), c["input_lengths"].cuda(), c["target_lengths"].cuda()
+    loss = op(x, tg, il, tl, reduction="mean", zero_infinity=True)
+    loss.backward()
+    g = x.grad
+    nll = op(x.detach(), tg, il, tl, reduction="none", zero_infinity=True)
+    infeasible = list(range(1, 9))                      # make_config("C4"): utterances 1..8 infeasible, 9..16 partial
+    assert torch.all(nll[infeasible] == 0) and torch.all(g[infeasible] == 0)
+    assert torch.all(nll[9:17] > 0) and torch.isfinite(nll).all() and torch.isfinite(g).all()
+    assert abs(loss.item() - (nll.double() / tl.clamp(min=1).double()).mean().item()) <= 1e-6 * abs(loss.item())
+    tmask = torch.arange(T, device="cuda")[None, :] < il[:, None]
+    assert torch.all(g[~tmask] == 0)
+    assert g.sum(-1)[tmask].abs().max().item() < 1e-5
+    idx = [0, 9, 40]
+    sub = {k: v[idx] for k, v in c.items()}
+    _, n64, g64 = ctc_c_f64(*[sub[k].numpy() for k in ("logits", "targets", "input_lengths", "target_lengths")],
+                            reduction="sum", zero_infinity=True)
+    assert np.abs(nll[idx].cpu().numpy() - n64).max() / np.abs(n64).max() < REL_LOSS
+    scale = 1.0 / (B * tl[idx].clamp(min=1).double().cpu().numpy())
+    assert np.abs(g[idx].cpu().numpy() - g64 * scale[:, None, None]).max() < ABS_GRAD
+
+
 def test_reduction_none_with_upstream_gradient():
     c = make_case(5, 40, 29, 8, 77)
     go = torch.tensor([0.5, -1.0, 2.0, 0.0, 1.5])
