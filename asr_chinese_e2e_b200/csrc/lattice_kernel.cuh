@@ -21,6 +21,12 @@
 // A CTA holds TWO utterances (4 warps) because warp w of a CTA always lands on SM sub-partition
 // w % 4: this gives every recursion warp its own issue port and MUFU unit.
 //
+// Precision: alpha/beta are kept RELATIVE to a running per-direction offset (a double, warp-uniform) that
+// absorbs the warp maximum once per stage, so the fp32 state stays within a few hundred log2 units of 0
+// instead of growing like T*log2(V) (|alpha| ~ 5000 at T=400): the stored halves, the occupancies and the
+// log-likelihood then carry ~30x less rounding error than a plain fp32 log-space recursion (torch's).
+// The offset of each stored stage is kept in tile_off[b][stage].
+//
 // The frames of lp_lab (and, in phase 2, the stored rows of the other direction) are staged in
 // shared memory by 1-D bulk TMA copies, TT frames per stage, a private ring of stages per warp,
 // completion on mbarriers.
@@ -43,10 +49,10 @@ struct LatCfg {
     static constexpr uint32_t AB_ROW = Sp * 4;
     static constexpr uint32_t STAGE = kLatTT * (LP_ROW + (GRAD ? AB_ROW : 0));
     static constexpr uint32_t RING = NSTG * STAGE;
-    // [4 rings][4*NSTG mbarriers][xch: 2 x (ll2 + pad)][bx: 2 x Sp floats (loss-only exchange)]
+    // [4 rings][4*NSTG mbarriers][xch: 2 x {double ll2, float ll2_rel, double beta offset}][bx: 2 x Sp floats]
     static constexpr uint32_t OFF_BARS = 4 * RING;
     static constexpr uint32_t OFF_XCH = OFF_BARS + 4 * NSTG * 8;
-    static constexpr uint32_t OFF_BX = OFF_XCH + 32;
+    static constexpr uint32_t OFF_BX = OFF_XCH + 64;
     static constexpr uint32_t SMEM = OFF_BX + (GRAD ? 0 : 2 * AB_ROW);
 };
 
@@ -165,13 +171,14 @@ __device__ __forceinline__ void lattice_dir(unsigned char *smem, int pair, int l
                                             const int64_t *__restrict__ targets, int64_t tnumel, int64_t toff,
                                             int *__restrict__ flags, const float *__restrict__ lp_lab,
                                             float *__restrict__ gam, float *__restrict__ ab_ws,
-                                            float *__restrict__ nll, int T, int zero_inf) {
+                                            float *__restrict__ nll, int T, int zero_inf,
+                                            double *__restrict__ tile_off) {
     using C = LatCfg<NS, GRAD>;
     constexpr int NL = C::NL, Lp = C::Lp, Sp = C::Sp, TT = kLatTT, NSTG = C::NSTG;
     const int wq = pair * 2 + DIR;                               // ring / barrier set of this warp
     const uint32_t ring = smem_u32(smem) + wq * C::RING;
     const uint32_t bar0 = smem_u32(smem) + C::OFF_BARS + wq * NSTG * 8;
-    const uint32_t xch = smem_u32(smem) + C::OFF_XCH + pair * 16;
+    const uint32_t xch = smem_u32(smem) + C::OFF_XCH + pair * 32;
     const uint32_t bx = smem_u32(smem) + C::OFF_BX + pair * C::AB_ROW;
     const int bar_id = 1 + pair;
 
@@ -207,6 +214,23 @@ __device__ __forceinline__ void lattice_dir(unsigned char *smem, int pair, int l
     }
 #pragma unroll
     for (int j = 0; j < NS; ++j) L.st[j] = kNeg;
+    double off = 0.0;                                            // true value = L.st[j] + off
+    // Once per stage the state is shifted by (roughly) its warp maximum and the shift is folded into `off`.
+    // Any shift is exact bookkeeping, so the maximum is taken from a snapshot at the START of the stage: its
+    // shuffle butterfly is independent of the recursion and is scheduled into the stage's idle issue slots.
+    auto snapshot_max = [&]() -> float {
+        float m = L.st[0];
+#pragma unroll
+        for (int j = 1; j < NS; ++j) m = fmaxf(m, L.st[j]);
+        return warp_max(m);
+    };
+    auto renorm = [&](float m) {
+        if (m > kNegTest) {
+#pragma unroll
+            for (int j = 0; j < NS; ++j) L.st[j] -= m;           // the -1e30 sentinel absorbs this
+            off += (double)m;
+        }
+    };
 
     // ---- tiling of time ----
     const int Qtot = (Tb + TT - 1) / TT;
@@ -218,6 +242,7 @@ __device__ __forceinline__ void lattice_dir(unsigned char *smem, int pair, int l
     const float *lp_base = lp_lab + (size_t)b * T * Lp;
     float *ab_base = ab_ws + (size_t)b * T * Sp;
     float *gam_base = gam + (size_t)b * T * Lp;
+    double *toff_base = tile_off + (size_t)b * ((T + TT - 1) / TT);
 
     auto issue = [&](int n) {                                    // lane 0 only
         const int q = DIR ? (Qtot - 1 - n) : n;
@@ -242,6 +267,7 @@ __device__ __forceinline__ void lattice_dir(unsigned char *smem, int pair, int l
         const int t0 = q * TT;
         const int rows = (Tb - t0) < TT ? (Tb - t0) : TT;
         const uint32_t tile = ring + stg * C::STAGE;
+        const float m_snap = snapshot_max();
         if (rows == TT) {                                        // full stage: straight-line, no per-step branch
 #pragma unroll
             for (int r = 0; r < TT; ++r) {
@@ -261,6 +287,8 @@ __device__ __forceinline__ void lattice_dir(unsigned char *smem, int pair, int l
         }
         __syncwarp();
         if (n_issue < n1) { if (lane == 0) issue(n_issue); ++n_issue; }
+        if (GRAD && lane == 0) toff_base[q] = off;               // offset of the rows just stored
+        renorm(m_snap);
     }
     // ================= midpoint =================
     if (GRAD) fence_proxy_async_global();                        // our stored rows -> the other warp's TMA reads
@@ -268,18 +296,25 @@ __device__ __forceinline__ void lattice_dir(unsigned char *smem, int pair, int l
 #pragma unroll
         for (int j = 0; j < NS; ++j)
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(bx + 4 * (NS * lane + j)), "f"(L.st[j]) : "memory");
+        if (lane == 0) asm volatile("st.shared.f64 [%0], %1;" ::"r"(xch + 16), "d"(off) : "memory");
     }
     named_bar_sync(bar_id, 64);
 
     // ================= phase 2: recursion + occupancies =================
     for (; n_issue < n1 + NSTG && n_issue < ntot; ++n_issue) if (lane == 0) issue(n_issue);
-    float ll2 = 0.f;
+    double ll2d = 0.0;                                           // log2-likelihood (true value)
+    float K = 0.f;                                               // off + other offset - ll2d for the current stage
     bool infeasible = false;
     if (DIR == 1) {                                              // alpha publishes ll2 at its first phase-2 step
         named_bar_sync(bar_id, 64);
-        ll2 = lds_f32(xch);
-        infeasible = ll2 < kNegTest;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(ll2d) : "r"(xch));
+        infeasible = lds_f32(xch + 8) < kNegTest;
     }
+    auto other_off = [&](int n) -> double {                      // offset of the other direction's stored stage of job n
+        if (!GRAD) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(xch + 16)); return v; }
+        return toff_base[DIR ? (Qtot - 1 - n) : n];
+    };
+    double other = (n1 < ntot && !infeasible) ? other_off(n1) : 0.0;
     int n_waited = n1;                                           // jobs [n_waited, n_issue) are still in flight
     for (int n = n1; n < ntot && !infeasible; ++n) {
         const int stg = n % NSTG;
@@ -289,6 +324,10 @@ __device__ __forceinline__ void lattice_dir(unsigned char *smem, int pair, int l
         const int t0 = q * TT;
         const int rows = (Tb - t0) < TT ? (Tb - t0) : TT;
         const uint32_t tile = ring + stg * C::STAGE;
+        const double other_cur = other;
+        if (n + 1 < ntot) other = other_off(n + 1);              // prefetch the next stage's offset
+        const float m_snap = snapshot_max();
+        K = (float)(off + other_cur - ll2d);
         // one phase-2 step: recursion, then gamma = 2^(alpha+beta-lp-ll2); returns this lane's blank part
         auto step2 = [&](int rr, bool first) -> float {
             const uint32_t fa = tile + rr * C::LP_ROW;
@@ -308,22 +347,26 @@ __device__ __forceinline__ void lattice_dir(unsigned char *smem, int pair, int l
 #pragma unroll
                 for (int j = 0; j < NS; ++j) sm += ex2f(e[j] - m);
                 sm = warp_sum(sm);
-                ll2 = m + lg2f(sm);
-                infeasible = ll2 < kNegTest;
+                const float ll2_rel = m + lg2f(sm);              // relative to the two offsets
+                infeasible = ll2_rel < kNegTest;
+                ll2d = off + other_cur + (double)ll2_rel;
+                K = -ll2_rel;
                 if (lane == 0) {
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch), "f"(ll2) : "memory");
-                    nll[b] = infeasible ? (zero_inf ? 0.f : __int_as_float(0x7f800000)) : -ll2 * kLn2;
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(xch), "d"(ll2d) : "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch + 8), "f"(ll2_rel) : "memory");
+                    nll[b] = infeasible ? (zero_inf ? 0.f : __int_as_float(0x7f800000))
+                                        : (float)(-ll2d * 0.6931471805599453);
                     flags[b] = infeasible ? 1 : 0;
                 }
                 named_bar_sync(bar_id, 64);
             }
             float gb = 0.f;
             if (GRAD && !infeasible) {
-                const float cb = lpb + ll2;
+                const float cb = lpb - K;
                 float gl[NL];
 #pragma unroll
                 for (int j = 0; j < NS; ++j) {
-                    const float c = (j & 1) ? (lpl[j >> 1] + ll2) : cb;
+                    const float c = (j & 1) ? (lpl[j >> 1] - K) : cb;
                     const float g = ex2f((L.st[j] + ot[j]) - c);
                     if (j & 1) gl[j >> 1] = g; else gb += g;
                 }
@@ -365,6 +408,7 @@ __device__ __forceinline__ void lattice_dir(unsigned char *smem, int pair, int l
         if (!GRAD || infeasible) break;
         __syncwarp();
         if (n_issue < ntot) { if (lane == 0) issue(n_issue); ++n_issue; }
+        renorm(m_snap);
     }
     // never leave the CTA with bulk copies still landing in its shared memory
     for (int n = n_waited; n < n_issue; ++n) mbar_wait(bar0 + 8 * (n % NSTG), (n / NSTG) & 1);
@@ -376,7 +420,8 @@ k2_lattice(const int64_t *__restrict__ targets, int64_t tnumel, const int *__res
            const int *__restrict__ Ub_arr, const int64_t *__restrict__ toff_arr, int *__restrict__ flags,
            const float *__restrict__ lp_lab, float *__restrict__ gam, float *__restrict__ ab_ws,
            float *__restrict__ nll, float *__restrict__ loss_sums, unsigned *__restrict__ ticket, int B,
-           int T, int zero_inf, float *__restrict__ zero_grad, const int *__restrict__ rowstart, int V) {
+           int T, int zero_inf, float *__restrict__ zero_grad, const int *__restrict__ rowstart, int V,
+           double *__restrict__ tile_off) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_lat = (B + 1) / 2;
@@ -396,10 +441,10 @@ k2_lattice(const int64_t *__restrict__ targets, int64_t tnumel, const int *__res
         const int64_t toff = toff_arr[b];
         if (dir == 0)
             lattice_dir<NS, GRAD, 0>(smem, pair, lane, b, Tb, Ub, targets, tnumel, toff, flags, lp_lab, gam, ab_ws,
-                                     nll, T, zero_inf);
+                                     nll, T, zero_inf, tile_off);
         else
             lattice_dir<NS, GRAD, 1>(smem, pair, lane, b, Tb, Ub, targets, tnumel, toff, flags, lp_lab, gam, ab_ws,
-                                     nll, T, zero_inf);
+                                     nll, T, zero_inf, tile_off);
     } else if (dir == 0 && lane == 0) {
         // no frames: empty target -> probability 1, anything else is infeasible (torch: inf, zero grad)
         nll[b] = (Ub == 0) ? 0.f : (zero_inf ? 0.f : __int_as_float(0x7f800000));

@@ -45,6 +45,7 @@ struct Workspace {
     size_t gam;       // float[B*T*Lp]
     size_t ab;        // float[B*T*Sp]
     size_t best;      // int[B*T]   per-frame argmax class (greedy CTC path), written by the sweep
+    size_t tile_off;  // double[B*ceil(T/8)] running offset of each stored 8-frame stage of the lattice
     size_t total;
 };
 
@@ -62,6 +63,7 @@ static inline Workspace workspace_layout(int B, int T, const Geom &g) {
     w.gam = o;       o += align_up(sizeof(float) * b * T * g.Lp);
     w.ab = o;        o += align_up(sizeof(float) * b * T * g.Sp);
     w.best = o;      o += align_up(sizeof(int) * b * T);
+    w.tile_off = o;  o += align_up(sizeof(double) * b * ((size_t)(T + 7) / 8));
     w.total = o;
     return w;
 }

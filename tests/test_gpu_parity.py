@@ -164,6 +164,28 @@ def test_c4_full_size_properties():
     assert np.abs(g[idx].cpu().numpy() - g64 * scale[:, None, None]).max() < ABS_GRAD
 
 
+def test_closer_to_float64_than_the_fp32_reference():
+    """The lattice keeps alpha/beta relative to a running offset (double), so its fp32 state stays small; the
+    un-normalised gradient and the loss must be at least as close to the float64 oracle as torch's fp32 path
+    (measured: 30-60x closer, profiles/r01_accuracy_vs_float64.txt)."""
+    c = make_case(6, 400, 4234, 50, 5, dist="D1")
+    a = [c[k].numpy() for k in ("logits", "targets", "input_lengths", "target_lengths")]
+    _, n64, g64 = ctc_c_f64(*a, reduction="sum")
+    rn, _ = ref_ctc(c["logits"], c["targets"], c["input_lengths"], c["target_lengths"], reduction="none", want_grad=False)
+    _, rg = ref_ctc(c["logits"], c["targets"], c["input_lengths"], c["target_lengths"], reduction="sum")
+    for fused in (True, False):
+        x = c["logits"].cuda().requires_grad_(True)
+        nll = _op()(x, c["targets"].cuda(), c["input_lengths"].cuda(), c["target_lengths"].cuda(), reduction="none",
+                    fused=fused)
+        nll.sum().backward()
+        ours_n = np.abs(nll.detach().cpu().numpy() - n64).max() / np.abs(n64).max()
+        ours_g = np.abs(x.grad.cpu().numpy() - g64).max()
+        ref_n = np.abs(rn.numpy() - n64).max() / np.abs(n64).max()
+        ref_g = np.abs(rg.numpy() - g64).max()
+        assert ours_n <= max(ref_n, 1.5e-7), (ours_n, ref_n)
+        assert ours_g <= 0.25 * ref_g, (ours_g, ref_g)
+
+
 def test_reduction_none_with_upstream_gradient():
     c = make_case(5, 40, 29, 8, 77)
     go = torch.tensor([0.5, -1.0, 2.0, 0.0, 1.5])

@@ -26,7 +26,7 @@ def layout(B, T, Umax):
     o, off = 0, {}
     for name, n in (("hdr", 256), ("Tb", 4 * B), ("Ub", 4 * B), ("flags", 4 * B), ("toff", 8 * B),
                     ("rowstart", 4 * (B + 1)), ("lp_lab", 4 * B * T * Lp), ("gam", 4 * B * T * Lp),
-                    ("ab", 4 * B * T * Sp)):
+                    ("ab", 4 * B * T * Sp), ("best", 4 * B * T), ("tile_off", 8 * B * ((T + 7) // 8))):
         off[name] = o
         o += align(n)
     return NS, Lp, Sp, off, o
