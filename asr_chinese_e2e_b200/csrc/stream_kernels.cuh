@@ -564,7 +564,7 @@ k3p_patch(const int64_t *__restrict__ targets, int64_t tnumel, const int *__rest
           const int *__restrict__ Ub_arr, const int64_t *__restrict__ toff_arr, const int *__restrict__ flags,
           const int *__restrict__ rowstart, const float *__restrict__ gam, float *__restrict__ grad,
           int reduction, float inv_batch, int B, int T, int V, int Lp, int blank, int zero_inf) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     int *pcls = (int *)smem;                  // [Lp] class of patch slot k (0 = blank, k>=1: label k-1)
     int *pnext = pcls + Lp;                   // [Lp] next slot with the same class, or -1
     const int tid = threadIdx.x;
