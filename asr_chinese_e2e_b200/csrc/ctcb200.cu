@@ -148,14 +148,14 @@ template <int NS, bool GRAD>
 cudaError_t launch_k2(cudaStream_t s, const int64_t *targets, int64_t tnumel, const int *Tb, const int *Ub,
                       const int64_t *toff, int *flags, const float *lp_lab, float *gam, float *ab, float *nll,
                       float *loss_sums, unsigned *ticket, int B, int T, int zero_inf, float *zero_grad,
-                      const int *rowstart, int V, int zero_ctas, double *tile_off) {
+                      const int *rowstart, int V, int zero_ctas, double *tile_off, float mean_scale) {
     using C = LatCfg<NS, GRAD>;
     cudaError_t e = cudaFuncSetAttribute(k2_lattice<NS, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::SMEM);
     if (e != cudaSuccess) return e;
     k2_lattice<NS, GRAD><<<(B + 1) / 2 + (zero_grad ? zero_ctas : 0), 128, C::SMEM, s>>>(
         targets, tnumel, Tb, Ub, toff, flags, lp_lab, gam, ab, nll, loss_sums, ticket, B, T, zero_inf, zero_grad,
-        rowstart, V, tile_off);
+        rowstart, V, tile_off, mean_scale);
     return cudaGetLastError();
 }
 
@@ -240,7 +240,7 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     unsigned *ticket = (unsigned *)(hdr + 1);
 #define K2_ARGS s, targets, tnumel, Tb, Ub, toff, flags, lp_lab, gam, ab, nll, loss_sums, ticket, B, T, zero_infinity, \
                 (zero_in_lattice ? fg->grad : nullptr), rowstart, V, dev.sms * env_int("CTCB200_ZERO_CPS", 2),   \
-                (double *)(ws + w.tile_off)
+                (double *)(ws + w.tile_off), (fused ? fg->inv_batch : 1.f / (float)B)
     if (want_grad) {
         if (g.NS == 4) e = launch_k2<4, true>(K2_ARGS);
         else if (g.NS == 8) e = launch_k2<8, true>(K2_ARGS);

@@ -421,7 +421,7 @@ k2_lattice(const int64_t *__restrict__ targets, int64_t tnumel, const int *__res
            const float *__restrict__ lp_lab, float *__restrict__ gam, float *__restrict__ ab_ws,
            float *__restrict__ nll, float *__restrict__ loss_sums, unsigned *__restrict__ ticket, int B,
            int T, int zero_inf, float *__restrict__ zero_grad, const int *__restrict__ rowstart, int V,
-           double *__restrict__ tile_off) {
+           double *__restrict__ tile_off, float mean_scale) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_lat = (B + 1) / 2;
@@ -467,7 +467,10 @@ k2_lattice(const int64_t *__restrict__ targets, int64_t tnumel, const int *__res
             }
             s_norm = warp_sum(s_norm);
             s_sum = warp_sum(s_sum);
-            if (lane == 0) { loss_sums[0] = s_norm; loss_sums[1] = s_sum; loss_sums[2] = (float)B; *ticket = 0; }
+            if (lane == 0) {
+                loss_sums[0] = s_norm; loss_sums[1] = s_sum; loss_sums[2] = (float)B; loss_sums[3] = s_norm * mean_scale;
+                *ticket = 0;
+            }
         }
     }
 }

@@ -102,6 +102,17 @@ def _event_handle(ev):
     return ev.cuda_event
 
 
+_ONES = {}
+
+
+def _ones(dev, n):
+    """Read-only ones[n] per device (the 'gradient already applied for upstream 1' marker): no fill kernel per call."""
+    key = (dev.type, dev.index, n)
+    if key not in _ONES:
+        _ONES[key] = torch.ones(n, dtype=torch.float32, device=dev)
+    return _ONES[key]
+
+
 def _n_chunks(B, requested):
     n = requested if requested is not None else int(os.environ.get("CTCB200_CHUNKS", "1"))
     return max(1, min(int(n), B)) if B else 1
@@ -139,7 +150,7 @@ def _two_sweep_pipeline(ctx, L, x, tg, stride, il, tl, B, T, V, umax, blank, zi,
     ws_bytes = [_lib.workspace_bytes(bounds[c + 1] - bounds[c], T, V, umax) for c in range(n_ch)]
     ws_off = [sum(ws_bytes[:c]) for c in range(n_ch)]
     ws = torch.empty(sum(ws_bytes), dtype=torch.uint8, device=dev)
-    sums = torch.zeros(n_ch, 3, dtype=torch.float32, device=dev)
+    sums = torch.empty(n_ch, 4, dtype=torch.float32, device=dev) if B else torch.zeros(n_ch, 4, device=dev)
     xs = 4 * T * V
 
     def call(c, stages, stream):
@@ -147,7 +158,7 @@ def _two_sweep_pipeline(ctx, L, x, tg, stride, il, tl, B, T, V, umax, blank, zi,
         _lib.check(L.ctcb200_loss_grad_stages(
             stages, x.data_ptr() + lo * xs, tg.data_ptr() + lo * stride * 8, stride, tg.numel() - lo * stride,
             il.data_ptr() + lo * 8, tl.data_ptr() + lo * 8, n, T, V, umax, blank, zi, red, inv_b,
-            nll.data_ptr() + lo * 4, sums.data_ptr() + c * 12, grad.data_ptr() + lo * xs,
+            nll.data_ptr() + lo * 4, sums.data_ptr() + c * 16, grad.data_ptr() + lo * xs,
             ws.data_ptr() + ws_off[c], ws_bytes[c], stream.cuda_stream), "ctcb200_loss_grad_stages")
 
     with torch.cuda.device(dev):
@@ -174,13 +185,14 @@ def _two_sweep_pipeline(ctx, L, x, tg, stride, il, tl, B, T, V, umax, blank, zi,
             _decode_chunks(L, decode, tg, stride, [(bounds[c], bounds[c + 1] - bounds[c], ws.data_ptr() + ws_off[c],
                                                     ws_bytes[c]) for c in range(n_ch)], T, V, umax, blank, main, dev, B)
     ctx.cfg = (stride, B, T, V, umax, blank, zi, red, 0, 0, n_ch, inv_b, True)
-    ctx.applied = torch.ones(B, dtype=torch.float32, device=dev)
+    ctx.applied = _ones(dev, B)
     ctx.save_for_backward(grad)
     if reduction == "none":
         return nll
+    if n_ch == 1:                                     # the lattice kernel already reduced (and scaled) the batch
+        return sums[0, 1] if reduction == "sum" else sums[0, 3]
     col = sums[:, 1] if reduction == "sum" else sums[:, 0]
-    tot = col[0] if n_ch == 1 else col.sum()
-    return tot if reduction == "sum" else tot * inv_b
+    return col.sum() if reduction == "sum" else col.sum() * inv_b
 
 
 class _CTCLossB200Fn(torch.autograd.Function):
@@ -217,7 +229,7 @@ class _CTCLossB200Fn(torch.autograd.Function):
         ws_bytes = _lib.workspace_bytes(max(per, 1), T, V, umax)
         ws = torch.empty(n_ch * ws_bytes, dtype=torch.uint8, device=dev)
         one = torch.ones((), dtype=torch.float32, device=dev) if fused else None
-        sums = torch.zeros(n_ch, 3, dtype=torch.float32, device=dev)   # per chunk: [sum nll/U, sum nll, n]
+        sums = torch.zeros(n_ch, 4, dtype=torch.float32, device=dev)   # per chunk: [sum nll/U, sum nll, n, mean]
         fwd = L.ctcb200_forward if need_grad else L.ctcb200_loss_only
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream()
@@ -249,11 +261,11 @@ class _CTCLossB200Fn(torch.autograd.Function):
                 args = (x.data_ptr() + lo * xs, tgp, stride, tg.numel() - lo * stride, il.data_ptr() + lo * 8,
                         tl.data_ptr() + lo * 8, n, T, V, umax, int(blank), zi)
                 if fused and two_sweep:
-                    _lib.check(L.ctcb200_loss_grad(*args, red, inv_b, nll.data_ptr() + lo * es, sums.data_ptr() + c * 12,
+                    _lib.check(L.ctcb200_loss_grad(*args, red, inv_b, nll.data_ptr() + lo * es, sums.data_ptr() + c * 16,
                                                    grad.data_ptr() + lo * xs, wsp, ws_bytes, st,
                                                    _event_handle(sweep_ev)), "ctcb200_loss_grad")
                     continue
-                _lib.check(fwd(*args, nll.data_ptr() + lo * es, sums.data_ptr() + c * 12, wsp, ws_bytes, st,
+                _lib.check(fwd(*args, nll.data_ptr() + lo * es, sums.data_ptr() + c * 16, wsp, ws_bytes, st,
                                _event_handle(sweep_ev)),
                            "ctcb200_forward" if need_grad else "ctcb200_loss_only")
                 if fused:
@@ -275,7 +287,7 @@ class _CTCLossB200Fn(torch.autograd.Function):
         ctx.cfg = (stride, B, T, V, umax, int(blank), zi, red, ws_bytes, per, n_ch, inv_b, fused)
         if need_grad:
             if fused:
-                ctx.applied = torch.ones(B, dtype=torch.float32, device=dev)
+                ctx.applied = _ones(dev, B)
                 ctx.save_for_backward(grad)
             else:
                 ctx.save_for_backward(x, tg, ws)

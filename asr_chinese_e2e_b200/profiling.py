@@ -21,7 +21,7 @@ def time_stages(logits, targets, input_lengths, target_lengths, blank=0, reducti
     ws_bytes = _lib.workspace_bytes(B, T, V, umax)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
     nll = torch.empty(B, device=x.device)
-    sums = torch.zeros(3, device=x.device)
+    sums = torch.zeros(4, device=x.device)
     grad = torch.empty_like(x)
     out = {"sweep_ms": [], "rest_ms": []}
     with torch.cuda.device(x.device):

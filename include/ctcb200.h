@@ -84,8 +84,9 @@ int ctcb200_workspace_bytes(int B, int T, int V, int Umax, size_t *out_bytes);
 /* Forward for training (replaces F.log_softmax + aten::_ctc_loss):
  *   prep + fused log-softmax/label-gather sweep + alpha/beta lattice recursion.
  * Writes nll[B] (per-utterance negative log-likelihood, zero_infinity applied) and, if
- * loss_sums != NULL, loss_sums[3] = { sum_b nll_b / max(U_b,1), sum_b nll_b, B }
- * (the 2-element normaliser pair a data-parallel all-reduce combines).
+ * loss_sums != NULL, loss_sums[4] = { sum_b nll_b / max(U_b,1), sum_b nll_b, B, 'mean' loss }
+ * ([0],[2]: the normaliser pair a data-parallel all-reduce combines; [3] = [0]/B, or
+ * [0]*inv_batch in ctcb200_loss_grad).
  * Leaves the state occupancies in `workspace` for ctcb200_backward.
  * targets_stride: row stride of the [B,Umax] target matrix, or 0 for 1-D concatenated
  * targets (then targets_numel bounds the reads).

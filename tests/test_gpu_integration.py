@@ -60,7 +60,7 @@ def test_stage_split_abi_equals_single_call():
 
     def run(stage_list):
         ws = torch.zeros(wsb, dtype=torch.uint8, device="cuda")
-        nll = torch.empty(B, device="cuda"); sums = torch.zeros(3, device="cuda"); grad = torch.full_like(x, 7.0)
+        nll = torch.empty(B, device="cuda"); sums = torch.zeros(4, device="cuda"); grad = torch.full_like(x, 7.0)
         for stg in stage_list:
             rc = L.ctcb200_loss_grad_stages(stg, x.data_ptr(), tg.data_ptr(), U, tg.numel(), il.data_ptr(),
                                             tl.data_ptr(), B, T, V, U, 0, 1, 1, 1.0 / B, nll.data_ptr(),
@@ -129,7 +129,7 @@ def test_no_out_of_bounds_writes_guard_zones():
     for mode in ("two_sweep", "three_sweep", "loss_only"):
         graw, gbuf = guarded(B * T * V * 4)
         nraw, nbuf = guarded(B * 4)
-        sraw, sbuf = guarded(3 * 4)
+        sraw, sbuf = guarded(4 * 4)
         wraw, wbuf = guarded(wsb)
         assert gbuf.data_ptr() % 16 == 0 and wbuf.data_ptr() % 256 == 0
         if mode == "two_sweep":
@@ -146,7 +146,7 @@ def test_no_out_of_bounds_writes_guard_zones():
                                         U, 0, 1, gbuf.data_ptr(), wbuf.data_ptr(), wsb, st)
         assert rc == 0, _lib.strerror(rc)
         torch.cuda.synchronize()
-        for name, raw, n in (("grad", graw, B * T * V * 4), ("nll", nraw, B * 4), ("sums", sraw, 12), ("ws", wraw, wsb)):
+        for name, raw, n in (("grad", graw, B * T * V * 4), ("nll", nraw, B * 4), ("sums", sraw, 16), ("ws", wraw, wsb)):
             assert bool((raw[:G] == 0xA5).all()) and bool((raw[G + n:] == 0xA5).all()), f"{mode}: {name} guard zone written"
         if mode != "loss_only":
             grad = gbuf.view(torch.float32).view(B, T, V)

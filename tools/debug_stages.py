@@ -42,7 +42,7 @@ def main(B=5, T=37, V=53, Umax=9, seed=1, zi=0, dist="D1"):
     assert wsb == total, (wsb, total)
     ws = torch.zeros(wsb, dtype=torch.uint8, device="cuda")
     nll = torch.full((B,), -1.0, device="cuda")
-    sums = torch.zeros(3, device="cuda")
+    sums = torch.zeros(4, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     rc = L.ctcb200_forward(x.data_ptr(), tg.data_ptr(), tg.shape[1], tg.numel(), il.data_ptr(), tl.data_ptr(),
                            B, T, V, Umax, 0, zi, nll.data_ptr(), sums.data_ptr(), ws.data_ptr(), wsb, st, None)

@@ -13,7 +13,7 @@ L = _lib.lib()
 per = B // n_ch
 wsb = _lib.workspace_bytes(per, T, V, U)
 ws = torch.empty(n_ch * wsb, dtype=torch.uint8, device="cuda")
-nll = torch.empty(B, device="cuda"); sums = torch.zeros(n_ch, 3, device="cuda"); grad = torch.empty_like(x)
+nll = torch.empty(B, device="cuda"); sums = torch.zeros(n_ch, 4, device="cuda"); grad = torch.empty_like(x)
 side = (torch.cuda.Stream(), torch.cuda.Stream())
 ev = lambda: torch.cuda.Event(enable_timing=True)
 def run(record):
@@ -29,7 +29,7 @@ def run(record):
         es0 = ev(); es0.record(s)
         sw = ev(); sw.record(s)   # materialise handle
         rc = L.ctcb200_loss_grad(x.data_ptr() + lo*T*V*4, tg.data_ptr() + lo*U*8, U, tg.numel() - lo*U, il.data_ptr()+lo*8, tl.data_ptr()+lo*8,
-                                 per, T, V, U, 0, 0, 1, 1.0/B, nll.data_ptr()+lo*4, sums.data_ptr()+ci*12, grad.data_ptr()+lo*T*V*4,
+                                 per, T, V, U, 0, 0, 1, 1.0/B, nll.data_ptr()+lo*4, sums.data_ptr()+ci*16, grad.data_ptr()+lo*T*V*4,
                                  ws.data_ptr()+ci*wsb, wsb, s.cuda_stream, sw.cuda_event)
         assert rc == 0
         ee = ev(); ee.record(s)

@@ -14,13 +14,13 @@ cut = int(round(B * split / 2)) * 2
 bounds = [0, cut, B]
 wsb = [_lib.workspace_bytes(bounds[i+1]-bounds[i], T, V, U) for i in range(2)]
 ws = [torch.empty(w, dtype=torch.uint8, device="cuda") for w in wsb]
-nll = torch.empty(B, device="cuda"); sums = torch.zeros(2, 3, device="cuda"); grad = torch.empty_like(x)
+nll = torch.empty(B, device="cuda"); sums = torch.zeros(2, 4, device="cuda"); grad = torch.empty_like(x)
 side = torch.cuda.Stream(priority=-1 if os.environ.get('HIPRI','1')=='1' else 0)
 ev = lambda: torch.cuda.Event(enable_timing=True)
 def call(ci, stages, s):
     lo, n = bounds[ci], bounds[ci+1]-bounds[ci]
     rc = L.ctcb200_loss_grad_stages(stages, x.data_ptr()+lo*T*V*4, tg.data_ptr()+lo*U*8, U, tg.numel()-lo*U, il.data_ptr()+lo*8, tl.data_ptr()+lo*8,
-                                    n, T, V, U, 0, 0, 1, 1.0/B, nll.data_ptr()+lo*4, sums.data_ptr()+ci*12, grad.data_ptr()+lo*T*V*4,
+                                    n, T, V, U, 0, 0, 1, 1.0/B, nll.data_ptr()+lo*4, sums.data_ptr()+ci*16, grad.data_ptr()+lo*T*V*4,
                                     ws[ci].data_ptr(), wsb[ci], s.cuda_stream)
     assert rc == 0, rc
 def run(show):
