@@ -22,6 +22,7 @@ int env_int(const char *name, int dflt) {
     const char *s = getenv(name);
     return (s && *s) ? atoi(s) : dflt;
 }
+const int g_use_pdl = env_int("CTCB200_PDL", 0);   // bit 0: sweep after prep, bit 1: lattice after sweep, bit 2: patch after lattice
 
 struct DevInfo {
     int sms;
@@ -83,6 +84,20 @@ int stream_cfg(int V, uint32_t stage_extra, size_t fixed_extra, int sms, int dfl
     return 0;
 }
 
+// Launch with programmatic stream serialization (PDL): the kernel may be scheduled while its predecessor on
+// the stream drains; every such kernel calls griddep_wait() before touching the predecessor's results.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(int edge, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                       Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (g_use_pdl >> edge) & 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 struct K1Args {
     const float *logits; const int64_t *targets; int64_t tnumel; const int *Tb, *Ub; const int64_t *toff;
     const int *rowstart; float *lp_lab; int *hdr; int B, T, V, Lp, blank;
@@ -100,10 +115,9 @@ cudaError_t launch_k1x(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
     cudaError_t e = cudaFuncSetAttribute(k1_lse_gather<NT, MAXC, EXACT, FUSED>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
     if (e != cudaSuccess) return e;
-    k1_lse_gather<NT, MAXC, EXACT, FUSED><<<c.grid, NT, c.smem, s>>>(
-        a.logits, a.targets, a.tnumel, a.Tb, a.Ub, a.toff, a.rowstart, a.lp_lab, a.hdr, a.B, a.T, a.V, a.Lp,
-        a.blank, c.nst, c.slot_bytes, a.grad, a.reduction, a.inv_batch, a.best, a.zero_pad_here);
-    return cudaGetLastError();
+    return launch_pdl(0, k1_lse_gather<NT, MAXC, EXACT, FUSED>, dim3(c.grid), dim3(NT), c.smem, s, a.logits, a.targets,
+                      a.tnumel, a.Tb, a.Ub, a.toff, a.rowstart, a.lp_lab, a.hdr, a.B, a.T, a.V, a.Lp, a.blank, c.nst,
+                      c.slot_bytes, a.grad, a.reduction, a.inv_batch, a.best, a.zero_pad_here);
 }
 template <int NT, int MAXC, bool EXACT>
 cudaError_t launch_k1(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
@@ -153,10 +167,9 @@ cudaError_t launch_k2(cudaStream_t s, const int64_t *targets, int64_t tnumel, co
     cudaError_t e = cudaFuncSetAttribute(k2_lattice<NS, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::SMEM);
     if (e != cudaSuccess) return e;
-    k2_lattice<NS, GRAD><<<(B + 1) / 2 + (zero_grad ? zero_ctas : 0), 128, C::SMEM, s>>>(
-        targets, tnumel, Tb, Ub, toff, flags, lp_lab, gam, ab, nll, loss_sums, ticket, B, T, zero_inf, zero_grad,
-        rowstart, V, tile_off, mean_scale);
-    return cudaGetLastError();
+    return launch_pdl(1, k2_lattice<NS, GRAD>, dim3((B + 1) / 2 + (zero_grad ? zero_ctas : 0)), dim3(128), C::SMEM, s,
+                      targets, tnumel, Tb, Ub, toff, flags, lp_lab, gam, ab, nll, loss_sums, ticket, B, T, zero_inf,
+                      zero_grad, rowstart, V, tile_off, mean_scale);
 }
 
 struct FusedGrad {          // non-null grad => 2-sweep mode: the sweep writes g*softmax, k3p adds -g*occupancy
@@ -257,10 +270,8 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
         const int per = env_int("CTCB200_K3P_CPS", 32);
         const size_t smem = 2 * (size_t)g.Lp * 4;
         prefer_max_carveout(k3p_patch<64>);
-        k3p_patch<64><<<dev.sms * (per < 1 ? 1 : per), 64, smem, s>>>(targets, tnumel, Tb, Ub, toff, flags, rowstart, gam,
-                                                                       fg->grad, fg->reduction, fg->inv_batch, B, T, V,
-                                                                       g.Lp, blank, zero_infinity);
-        e = cudaGetLastError();
+        e = launch_pdl(2, k3p_patch<64>, dim3(dev.sms * (per < 1 ? 1 : per)), dim3(64), smem, s, targets, tnumel, Tb, Ub, toff,
+                       flags, rowstart, gam, fg->grad, fg->reduction, fg->inv_batch, B, T, V, g.Lp, blank, zero_infinity);
     }
     return (int)e;
 }

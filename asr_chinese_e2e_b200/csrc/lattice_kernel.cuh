@@ -424,6 +424,8 @@ k2_lattice(const int64_t *__restrict__ targets, int64_t tnumel, const int *__res
            double *__restrict__ tile_off, float mean_scale) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    griddep_wait();                                              // the sweep's lp_lab frames
+    griddep_launch_dependents();
     const int n_lat = (B + 1) / 2;
     if ((int)blockIdx.x >= n_lat) {
         // Extra CTAs of the same launch: while the (latency-bound) lattice CTAs run, these write the zeros of

@@ -86,6 +86,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may be scheduled while its
+// predecessor on the stream is still running; it must not touch the predecessor's results before
+// griddep_wait().  griddep_launch_dependents() in the predecessor allows that early scheduling, which hides
+// the launch latency and the CTA set-up of the next kernel behind the tail of this one.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- math -------------------------------------------------------------------------------------
 __device__ __forceinline__ float ex2f(float x) {
     float y;

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(1024) k0_prep(const int64_t *__restrict__ in_l
     __shared__ long long s_part[2][32];
     __shared__ long long s_carry[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    griddep_launch_dependents();
     if (tid == 0) { hdr[0] = 0; hdr[1] = 0; s_carry[0] = 0; s_carry[1] = 0; }
     __syncthreads();
     int bad = 0;
@@ -204,6 +205,8 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
               int *__restrict__ best, int zero_pad_here) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    griddep_wait();                                  // k0_prep's lengths / prefix sums
+    griddep_launch_dependents();
     int r0, nrows;
     grid_share(rowstart[B], r0, nrows);
     if (FUSED && zero_pad_here) zero_padded_frames<NT>(grad, Tb_arr, rowstart, B, T, V, tid);
@@ -568,6 +571,7 @@ k3p_patch(const int64_t *__restrict__ targets, int64_t tnumel, const int *__rest
     int *pcls = (int *)smem;                  // [Lp] class of patch slot k (0 = blank, k>=1: label k-1)
     int *pnext = pcls + Lp;                   // [Lp] next slot with the same class, or -1
     const int tid = threadIdx.x;
+    griddep_wait();                           // the lattice's occupancies, the sweep's dense gradient
     int r0, nrows;
     grid_share(rowstart[B], r0, nrows);
     if (nrows <= 0) return;
