@@ -62,6 +62,7 @@ SIGNATURES = {
     "ctcb200_ce_workspace_bytes": (_i, [_i64, ctypes.POINTER(_sz)]),
     "ctcb200_ce_loss_grad": (_i, [_p, _p, _i64, _i, _i, _f, _f, _p, _p, _p, _sz, _p]),
     "ctcb200_read_status": (_i, [_p, ctypes.POINTER(_i), _p]),
+    "ctcb200_read_lattice_stats": (_i, [_p, ctypes.POINTER(_i), _p]),
 }
 
 

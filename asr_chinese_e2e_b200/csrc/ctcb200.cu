@@ -7,7 +7,7 @@
 
 #include "ce_kernel.cuh"
 #include "decode_kernel.cuh"
-#include "lattice_kernel.cuh"
+#include "lattice_lin.cuh"
 #include "layout.h"
 #include "stream_kernels.cuh"
 
@@ -102,7 +102,7 @@ struct K1Args {
     const float *logits; const int64_t *targets; int64_t tnumel; const int *Tb, *Ub; const int64_t *toff;
     const int *rowstart; float *lp_lab; int *hdr; int B, T, V, Lp, blank;
     float *grad; int reduction; float inv_batch;   // fused (2-sweep) mode only
-    int *best; int zero_pad_here;
+    int *best; int zero_pad_here; int *slow; float lin_thr; float *p_lab;
 };
 struct K3Args {
     const float *logits; const int64_t *targets; int64_t tnumel; const int *Tb, *Ub; const int64_t *toff;
@@ -117,7 +117,7 @@ cudaError_t launch_k1x(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
     if (e != cudaSuccess) return e;
     return launch_pdl(0, k1_lse_gather<NT, MAXC, EXACT, FUSED>, dim3(c.grid), dim3(NT), c.smem, s, a.logits, a.targets,
                       a.tnumel, a.Tb, a.Ub, a.toff, a.rowstart, a.lp_lab, a.hdr, a.B, a.T, a.V, a.Lp, a.blank, c.nst,
-                      c.slot_bytes, a.grad, a.reduction, a.inv_batch, a.best, a.zero_pad_here);
+                      c.slot_bytes, a.grad, a.reduction, a.inv_batch, a.best, a.zero_pad_here, a.slow, a.lin_thr, a.p_lab);
 }
 template <int NT, int MAXC, bool EXACT>
 cudaError_t launch_k1(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
@@ -162,14 +162,14 @@ template <int NS, bool GRAD>
 cudaError_t launch_k2(cudaStream_t s, const int64_t *targets, int64_t tnumel, const int *Tb, const int *Ub,
                       const int64_t *toff, int *flags, const float *lp_lab, float *gam, float *ab, float *nll,
                       float *loss_sums, unsigned *ticket, int B, int T, int zero_inf, float *zero_grad,
-                      const int *rowstart, int V, int zero_ctas, double *tile_off, float mean_scale) {
-    using C = LatCfg<NS, GRAD>;
-    cudaError_t e = cudaFuncSetAttribute(k2_lattice<NS, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)C::SMEM);
+                      const int *rowstart, int V, int zero_ctas, double *tile_off, float mean_scale, const int *slow,
+                      size_t ab_utt, const float *p_lab) {
+    constexpr uint32_t smem = k2_smem_bytes<NS, GRAD>();
+    cudaError_t e = cudaFuncSetAttribute(k2_lattice<NS, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return launch_pdl(1, k2_lattice<NS, GRAD>, dim3((B + 1) / 2 + (zero_grad ? zero_ctas : 0)), dim3(128), C::SMEM, s,
+    return launch_pdl(1, k2_lattice<NS, GRAD>, dim3((B + 1) / 2 + (zero_grad ? zero_ctas : 0)), dim3(128), smem, s,
                       targets, tnumel, Tb, Ub, toff, flags, lp_lab, gam, ab, nll, loss_sums, ticket, B, T, zero_inf,
-                      zero_grad, rowstart, V, tile_off, mean_scale);
+                      zero_grad, rowstart, V, tile_off, mean_scale, slow, ab_utt, p_lab);
 }
 
 struct FusedGrad {          // non-null grad => 2-sweep mode: the sweep writes g*softmax, k3p adds -g*occupancy
@@ -204,8 +204,16 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     int *Tb = (int *)(ws + w.Tb), *Ub = (int *)(ws + w.Ub), *flags = (int *)(ws + w.flags);
     int64_t *toff = (int64_t *)(ws + w.toff);
     int *rowstart = (int *)(ws + w.rowstart);
+    int *slow = (int *)(ws + w.slow);
     float *lp_lab = (float *)(ws + w.lp_lab), *gam = (float *)(ws + w.gam), *ab = (float *)(ws + w.ab);
     const int64_t tnumel = targets_stride ? (int64_t)B * targets_stride : targets_numel;
+    // Range of the linear-domain lattice (lattice_lin.cuh): a stage of TT frames plus the NS/2 labels of one lane
+    // may shrink a value by (TT + NS/2) * |lp| binary orders; keep that inside ~900 of a double's 1022.
+    // CTCB200_LATTICE_LOG=1 forces the log-space recursion for every utterance.
+    static const int lattice_mode = env_int("CTCB200_LATTICE_LOG", 0);
+    static const int thr_env = env_int("CTCB200_LIN_THR", 0);
+    const float lin_thr = lattice_mode ? 1.f
+                                       : -(float)(thr_env > 0 ? thr_env : 900 / (lin_tile_frames(g.NS) + g.NS / 2));
 
     const bool fused = fg != nullptr;
     const int stages = fused ? fg->stages : 7;
@@ -218,7 +226,7 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     cudaError_t e = cudaSuccess;
     if (stages & 1) {
     prefer_max_carveout(k0_prep);
-    k0_prep<<<1, 1024, 0, s>>>(in_len, tgt_len, targets_stride, B, T, Umax, hdr, Tb, Ub, flags, toff, rowstart);
+    k0_prep<<<1, 1024, 0, s>>>(in_len, tgt_len, targets_stride, B, T, Umax, hdr, Tb, Ub, flags, toff, rowstart, slow);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
 
@@ -235,7 +243,7 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     {
         const K1Args a = {logits, targets, tnumel, Tb, Ub, toff, rowstart, lp_lab, hdr, B, T, V, g.Lp, blank,
                           fused ? fg->grad : nullptr, fused ? fg->reduction : 0, fused ? fg->inv_batch : 0.f,
-                          want_argmax ? (int *)(ws + w.best) : nullptr, zero_in_lattice ? 0 : 1};
+                          want_argmax ? (int *)(ws + w.best) : nullptr, zero_in_lattice ? 0 : 1, slow, lin_thr, (float *)(ws + w.p_lab)};
         if (fused) {
             if (nt1 == 64) e = STREAM_DISPATCH(launch_k1f, 64, rounds1, exact1, c, s, a);
             else e = STREAM_DISPATCH(launch_k1f, 128, rounds1, exact1, c, s, a);
@@ -253,7 +261,7 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     unsigned *ticket = (unsigned *)(hdr + 1);
 #define K2_ARGS s, targets, tnumel, Tb, Ub, toff, flags, lp_lab, gam, ab, nll, loss_sums, ticket, B, T, zero_infinity, \
                 (zero_in_lattice ? fg->grad : nullptr), rowstart, V, dev.sms * env_int("CTCB200_ZERO_CPS", 2),   \
-                (double *)(ws + w.tile_off), (fused ? fg->inv_batch : 1.f / (float)B)
+                (double *)(ws + w.tile_off), (fused ? fg->inv_batch : 1.f / (float)B), slow, w.ab_utt, (const float *)(ws + w.p_lab)
     if (want_grad) {
         if (g.NS == 4) e = launch_k2<4, true>(K2_ARGS);
         else if (g.NS == 8) e = launch_k2<8, true>(K2_ARGS);
@@ -521,6 +529,14 @@ int ctcb200_ce_loss_grad(const float *pred, const int64_t *gold, int64_t rows, i
 int ctcb200_read_status(const void *workspace, int *host_status, ctcb200_stream_t stream) {
     if (!workspace || !host_status) return CTCB200_ERR_NULL;
     cudaError_t e = cudaMemcpyAsync(host_status, workspace, sizeof(int), cudaMemcpyDeviceToHost,
+                                    (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaStreamSynchronize((cudaStream_t)stream);
+}
+
+int ctcb200_read_lattice_stats(const void *workspace, int *host_stats, ctcb200_stream_t stream) {
+    if (!workspace || !host_stats) return CTCB200_ERR_NULL;
+    cudaError_t e = cudaMemcpyAsync(host_stats, (const int *)workspace + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost,
                                     (cudaStream_t)stream);
     if (e != cudaSuccess) return (int)e;
     return (int)cudaStreamSynchronize((cudaStream_t)stream);

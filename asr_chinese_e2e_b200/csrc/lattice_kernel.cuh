@@ -49,11 +49,8 @@ struct LatCfg {
     static constexpr uint32_t AB_ROW = Sp * 4;
     static constexpr uint32_t STAGE = kLatTT * (LP_ROW + (GRAD ? AB_ROW : 0));
     static constexpr uint32_t RING = NSTG * STAGE;
-    // [4 rings][4*NSTG mbarriers][xch: 2 x {double ll2, float ll2_rel, double beta offset}][bx: 2 x Sp floats]
-    static constexpr uint32_t OFF_BARS = 4 * RING;
-    static constexpr uint32_t OFF_XCH = OFF_BARS + 4 * NSTG * 8;
-    static constexpr uint32_t OFF_BX = OFF_XCH + 64;
-    static constexpr uint32_t SMEM = OFF_BX + (GRAD ? 0 : 2 * AB_ROW);
+    // xch (per utterance, 32 B): {double ll2, float ll2_rel, double beta offset}; bx (loss only): Sp floats.
+    // The shared-memory map of the kernel is K2Smem in lattice_lin.cuh.
 };
 
 // log2(2^a + 2^b): 2 MUFU.  With the finite sentinel a-b is never inf-inf.
@@ -167,7 +164,8 @@ __device__ __forceinline__ void lat_step(LatLane<NS> &L, uint32_t fa, int t, flo
 }
 
 template <int NS, bool GRAD, int DIR>
-__device__ __forceinline__ void lattice_dir(unsigned char *smem, int pair, int lane, int b, int Tb, int Ub,
+__device__ __forceinline__ void lattice_dir(uint32_t ring, uint32_t bar0, uint32_t xch, uint32_t bx, int bar_id,
+                                            int lane, int b, int Tb, int Ub,
                                             const int64_t *__restrict__ targets, int64_t tnumel, int64_t toff,
                                             int *__restrict__ flags, const float *__restrict__ lp_lab,
                                             float *__restrict__ gam, float *__restrict__ ab_ws,
@@ -175,12 +173,8 @@ __device__ __forceinline__ void lattice_dir(unsigned char *smem, int pair, int l
                                             double *__restrict__ tile_off) {
     using C = LatCfg<NS, GRAD>;
     constexpr int NL = C::NL, Lp = C::Lp, Sp = C::Sp, TT = kLatTT, NSTG = C::NSTG;
-    const int wq = pair * 2 + DIR;                               // ring / barrier set of this warp
-    const uint32_t ring = smem_u32(smem) + wq * C::RING;
-    const uint32_t bar0 = smem_u32(smem) + C::OFF_BARS + wq * NSTG * 8;
-    const uint32_t xch = smem_u32(smem) + C::OFF_XCH + pair * 32;
-    const uint32_t bx = smem_u32(smem) + C::OFF_BX + pair * C::AB_ROW;
-    const int bar_id = 1 + pair;
+    // ring / bar0: this warp's private stage ring and its NSTG mbarriers; xch (32 B) / bx (one row): shared by
+    // the two warps of the utterance; bar_id: their named barrier
 
     if (lane == 0) {
         for (int s = 0; s < NSTG; ++s) mbar_init(bar0 + 8 * s, 1);
@@ -240,7 +234,7 @@ __device__ __forceinline__ void lattice_dir(unsigned char *smem, int pair, int l
     const int n1 = DIR ? (Qtot - Qm) : Qm;                       // phase-1 jobs of this warp
     const int ntot = GRAD ? Qtot : (DIR ? n1 : Qm + 1);
     const float *lp_base = lp_lab + (size_t)b * T * Lp;
-    float *ab_base = ab_ws + (size_t)b * T * Sp;
+    float *ab_base = ab_ws;                                      // this utterance's part of the scratch
     float *gam_base = gam + (size_t)b * T * Lp;
     double *toff_base = tile_off + (size_t)b * ((T + TT - 1) / TT);
 
@@ -412,69 +406,6 @@ __device__ __forceinline__ void lattice_dir(unsigned char *smem, int pair, int l
     }
     // never leave the CTA with bulk copies still landing in its shared memory
     for (int n = n_waited; n < n_issue; ++n) mbar_wait(bar0 + 8 * (n % NSTG), (n / NSTG) & 1);
-}
-
-template <int NS, bool GRAD>
-__global__ void __launch_bounds__(128)
-k2_lattice(const int64_t *__restrict__ targets, int64_t tnumel, const int *__restrict__ Tb_arr,
-           const int *__restrict__ Ub_arr, const int64_t *__restrict__ toff_arr, int *__restrict__ flags,
-           const float *__restrict__ lp_lab, float *__restrict__ gam, float *__restrict__ ab_ws,
-           float *__restrict__ nll, float *__restrict__ loss_sums, unsigned *__restrict__ ticket, int B,
-           int T, int zero_inf, float *__restrict__ zero_grad, const int *__restrict__ rowstart, int V,
-           double *__restrict__ tile_off, float mean_scale) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    griddep_wait();                                              // the sweep's lp_lab frames
-    griddep_launch_dependents();
-    const int n_lat = (B + 1) / 2;
-    if ((int)blockIdx.x >= n_lat) {
-        // Extra CTAs of the same launch: while the (latency-bound) lattice CTAs run, these write the zeros of
-        // the padded frames of grad -- HBM work of the step that would otherwise sit in the sweep kernel.
-        zero_padded_frames<128>(zero_grad, Tb_arr, rowstart, B, T, V, tid, (int)blockIdx.x - n_lat,
-                                (int)gridDim.x - n_lat);
-        return;
-    }
-    const int pair = warp >> 1, dir = warp & 1;
-    const int b = 2 * blockIdx.x + pair;
-    if (b >= B) return;                                          // odd batch: the last CTA has one utterance
-    const int Tb = Tb_arr[b], Ub = Ub_arr[b];
-
-    if (Tb > 0) {
-        const int64_t toff = toff_arr[b];
-        if (dir == 0)
-            lattice_dir<NS, GRAD, 0>(smem, pair, lane, b, Tb, Ub, targets, tnumel, toff, flags, lp_lab, gam, ab_ws,
-                                     nll, T, zero_inf, tile_off);
-        else
-            lattice_dir<NS, GRAD, 1>(smem, pair, lane, b, Tb, Ub, targets, tnumel, toff, flags, lp_lab, gam, ab_ws,
-                                     nll, T, zero_inf, tile_off);
-    } else if (dir == 0 && lane == 0) {
-        // no frames: empty target -> probability 1, anything else is infeasible (torch: inf, zero grad)
-        nll[b] = (Ub == 0) ? 0.f : (zero_inf ? 0.f : __int_as_float(0x7f800000));
-        flags[b] = (Ub != 0);
-    }
-
-    // ---- deterministic batch reduction by the last utterance to finish ----
-    if (loss_sums != nullptr && dir == 0) {
-        unsigned tk = 0;
-        if (lane == 0) { __threadfence(); tk = atomicAdd(ticket, 1u); }
-        tk = __shfl_sync(0xffffffffu, tk, 0);
-        if (tk == (unsigned)B - 1) {
-            __threadfence();
-            float s_norm = 0.f, s_sum = 0.f;
-            for (int i = lane; i < B; i += 32) {
-                const float v = __ldcg(nll + i);
-                const int u = Ub_arr[i];
-                s_sum += v;
-                s_norm += v / (float)(u > 1 ? u : 1);
-            }
-            s_norm = warp_sum(s_norm);
-            s_sum = warp_sum(s_sum);
-            if (lane == 0) {
-                loss_sums[0] = s_norm; loss_sums[1] = s_sum; loss_sums[2] = (float)B; loss_sums[3] = s_norm * mean_scale;
-                *ticket = 0;
-            }
-        }
-    }
 }
 
 }  // namespace ctcb200

@@ -30,6 +30,18 @@ static inline bool geom_for(int Umax, Geom *g) {
 // [4+j] label slot j (j < U_b; the finite log(0) sentinel -1e30 beyond).  In `gam` the same slots hold the posterior
 // state occupancies: [0] sum over all blank states, [4+j] label state of slot j.
 
+// Frames per stage of the linear-domain lattice (also its renormalisation interval).
+static inline int lin_tile_frames(int NS) { return NS == 16 ? 4 : 8; }
+// `ab` per utterance, linear-domain lattice: one block per stage = 32 lane exponents (int) followed by
+// up to TT rows of up to Sp doubles.  The log-space lattice uses the same area as float[T][Sp].
+static inline size_t lin_ab_utt_bytes(int T, const Geom &g) {
+    const size_t tt = (size_t)lin_tile_frames(g.NS);
+    const size_t lin = ((size_t)T + tt - 1) / tt * (128 + tt * (size_t)g.Sp * 8);
+    const size_t lg = (size_t)T * g.Sp * 4;
+    const size_t m = lin > lg ? lin : lg;
+    return (m + 127) / 128 * 128;
+}
+
 constexpr size_t kAlign = 256;
 static inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a; }
 
@@ -39,11 +51,14 @@ struct Workspace {
     size_t Tb;        // int[B]   clamped input lengths
     size_t Ub;        // int[B]   clamped target lengths
     size_t flags;     // int[B]   1 = infeasible (no valid alignment)
+    size_t slow;      // int[B]   1 = some gathered log-probability is outside the linear-domain lattice's range
     size_t toff;      // int64[B] element offset of utterance b's labels in `targets`
     size_t rowstart;  // int[B+1] exclusive prefix sum of Tb (valid-frame numbering)
     size_t lp_lab;    // float[B*T*Lp]
+    size_t p_lab;     // float[B*T*Lp]  the same frames as probabilities 2^lp (slot [1] again lse2): linear-domain lattice
     size_t gam;       // float[B*T*Lp]
-    size_t ab;        // float[B*T*Sp]
+    size_t ab;        // stored alpha/beta halves: B blocks of ab_utt bytes (see lin_ab_utt_bytes)
+    size_t ab_utt;    // bytes per utterance of `ab`
     size_t best;      // int[B*T]   per-frame argmax class (greedy CTC path), written by the sweep
     size_t tile_off;  // double[B*ceil(T/8)] running offset of each stored 8-frame stage of the lattice
     size_t total;
@@ -57,11 +72,14 @@ static inline Workspace workspace_layout(int B, int T, const Geom &g) {
     w.Tb = o;        o += align_up(sizeof(int) * b);
     w.Ub = o;        o += align_up(sizeof(int) * b);
     w.flags = o;     o += align_up(sizeof(int) * b);
+    w.slow = o;      o += align_up(sizeof(int) * b);
     w.toff = o;      o += align_up(sizeof(int64_t) * b);
     w.rowstart = o;  o += align_up(sizeof(int) * (b + 1));
     w.lp_lab = o;    o += align_up(sizeof(float) * b * T * g.Lp);
+    w.p_lab = o;     o += align_up(sizeof(float) * b * T * g.Lp);
     w.gam = o;       o += align_up(sizeof(float) * b * T * g.Lp);
-    w.ab = o;        o += align_up(sizeof(float) * b * T * g.Sp);
+    w.ab_utt = lin_ab_utt_bytes(T, g);
+    w.ab = o;        o += align_up(w.ab_utt * b);
     w.best = o;      o += align_up(sizeof(int) * b * T);
     w.tile_off = o;  o += align_up(sizeof(double) * b * ((size_t)(T + 7) / 8));
     w.total = o;

@@ -74,6 +74,9 @@ __device__ __forceinline__ void stg_v4_hint(float4 *p, float4 v, uint64_t policy
 __device__ __forceinline__ void stg_v2_hint(float2 *p, float2 v, uint64_t policy) {
     asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(policy) : "memory");
 }
+__device__ __forceinline__ void stg_v2f64_hint(double *p, double a, double b, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(a), "d"(b), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void stg_f32_hint(float *p, float v, uint64_t policy) {
     asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(policy) : "memory");
 }

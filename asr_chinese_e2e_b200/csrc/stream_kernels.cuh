@@ -30,12 +30,13 @@ __global__ void __launch_bounds__(1024) k0_prep(const int64_t *__restrict__ in_l
                                                 int64_t targets_stride, int B, int T, int Umax,
                                                 int *__restrict__ hdr, int *__restrict__ Tb_arr,
                                                 int *__restrict__ Ub_arr, int *__restrict__ flags,
-                                                int64_t *__restrict__ toff, int *__restrict__ rowstart) {
+                                                int64_t *__restrict__ toff, int *__restrict__ rowstart,
+                                                int *__restrict__ slow) {
     __shared__ long long s_part[2][32];
     __shared__ long long s_carry[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     griddep_launch_dependents();
-    if (tid == 0) { hdr[0] = 0; hdr[1] = 0; s_carry[0] = 0; s_carry[1] = 0; }
+    if (tid == 0) { hdr[0] = 0; hdr[1] = 0; hdr[2] = 0; hdr[3] = 0; s_carry[0] = 0; s_carry[1] = 0; }
     __syncthreads();
     int bad = 0;
     for (int base = 0; base < B; base += 1024) {
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(1024) k0_prep(const int64_t *__restrict__ in_l
             if (t < 0 || t > T) { bad |= 1; t = t < 0 ? 0 : T; }
             if (u < 0 || u > Umax) { bad |= 2; u = u < 0 ? 0 : Umax; }
             tb = t; ub = u;
-            Tb_arr[b] = (int)t; Ub_arr[b] = (int)u; flags[b] = 0;
+            Tb_arr[b] = (int)t; Ub_arr[b] = (int)u; flags[b] = 0; slow[b] = 0;
         }
         // block-wide inclusive scan of (tb, ub)
         long long st = tb, su = ub;
@@ -202,7 +203,8 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
               const int64_t *__restrict__ toff_arr, const int *__restrict__ rowstart,
               float *__restrict__ lp_lab, int *__restrict__ hdr, int B, int T, int V, int Lp, int blank,
               int nst, uint32_t slot_bytes, float *__restrict__ grad, int reduction, float inv_batch,
-              int *__restrict__ best, int zero_pad_here) {
+              int *__restrict__ best, int zero_pad_here, int *__restrict__ slow, float lin_thr,
+              float *__restrict__ p_lab) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     griddep_wait();                                  // k0_prep's lengths / prefix sums
@@ -363,14 +365,22 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
             best[(size_t)cc.b * T + cc.t] = NT == 128 ? min(min(ri[0], ri[1]), min(ri[2], ri[3])) : min(ri[0], ri[1]);
         }
         float *frame = lp_lab + ((size_t)cc.b * T + cc.t) * Lp;
+        float *pframe = p_lab + ((size_t)cc.b * T + cc.t) * Lp;
 #pragma unroll
         for (int kk = 0; kk < MAXG; ++kk) {
             const int k = tid + kk * NT;
             if (k < Lp) {
-                float o;
-                if (cg[kk] >= 0) o = fmaxf(fmaf(xg[kk], kLog2e, -lse2), kNeg);   // -inf logit -> sentinel
-                else o = cg[kk] == -2 ? lse2 : (cg[kk] == -3 ? 0.f : kNeg);
+                float o, pr;
+                if (cg[kk] >= 0) {
+                    o = fmaxf(fmaf(xg[kk], kLog2e, -lse2), kNeg);   // -inf logit -> sentinel
+                    pr = ex2f(o);
+                    if (!(o >= lin_thr)) slow[cc.b] = 1;            // (or NaN) outside the linear-domain lattice's range
+                } else {
+                    o = cg[kk] == -2 ? lse2 : (cg[kk] == -3 ? 0.f : kNeg);
+                    pr = cg[kk] == -2 ? lse2 : 0.f;
+                }
                 stg_f32_hint(frame + k, o, kEvictLast);           // re-read by the lattice kernel
+                stg_f32_hint(pframe + k, pr, kEvictLast);
             }
         }
         if (FUSED) {

@@ -181,6 +181,12 @@ int ctcb200_ce_loss_grad(const float *pred, const int64_t *gold, int64_t rows, i
 /* Debug: copies the device status word to *host_status (synchronises `stream`). */
 int ctcb200_read_status(const void *workspace, int *host_status, ctcb200_stream_t stream);
 
+/* Debug: which recursion the lattice kernel of the last call used (synchronises `stream`).
+ * host_stats[0] = utterances that ran the log-space recursion (the rest ran the faster linear-domain one),
+ * host_stats[1] = of those, utterances that were first tried in the linear domain and whose likelihood
+ * underflowed to zero there (this includes every infeasible utterance). */
+int ctcb200_read_lattice_stats(const void *workspace, int *host_stats, ctcb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

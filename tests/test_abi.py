@@ -26,7 +26,7 @@ def declared_symbols():
 def test_header_symbols_exported(lib):
     names = declared_symbols()
     assert {"ctcb200_forward", "ctcb200_backward", "ctcb200_loss_only", "ctcb200_workspace_bytes",
-            "ctcb200_strerror", "ctcb200_version", "ctcb200_read_status"} <= set(names)
+            "ctcb200_strerror", "ctcb200_version", "ctcb200_read_status", "ctcb200_read_lattice_stats"} <= set(names)
     for n in names:
         assert hasattr(lib, n), n
     assert set(_lib.SIGNATURES) == set(names)
@@ -34,9 +34,11 @@ def test_header_symbols_exported(lib):
 
 
 def test_workspace_bytes_is_host_arithmetic(lib):
-    # frames of 4+16*NS floats (NS=4 up to U=63), stored half-lattice rows of 32*NS floats, 1 int argmax per frame, 1 double per 8 frames
+    # frames of 4+16*NS floats (NS=4 up to U=63) for lp_lab, p_lab and gam, stored half-lattice stages of
+    # {32 lane exponents, 8 rows of 32*NS doubles}, 1 int argmax per frame, 1 double per 8 frames
     b = _lib.workspace_bytes(256, 400, 4234, 50)
-    assert 256 * 400 * (2 * 68 + 128 + 1) * 4 + 256 * 50 * 8 <= b <= 256 * 400 * (2 * 68 + 128 + 1) * 4 + 256 * 50 * 8 + 64 * 1024
+    want = 256 * 400 * (3 * 68 + 1) * 4 + 256 * 50 * (128 + 8 * 128 * 8) + 256 * 50 * 8
+    assert want <= b <= want + 64 * 1024
     assert _lib.workspace_bytes(64, 1500, 4234, 120) > 64 * 1500 * (2 * 132 + 256) * 4
     out = ctypes.c_size_t(0)
     assert lib.ctcb200_workspace_bytes(1, 1, 5, 256, ctypes.byref(out)) == -4      # Umax > 255

@@ -300,3 +300,81 @@ def test_error_codes_and_no_cpu_fallback():
         op(torch.zeros(1, 4, 5, device="cuda", dtype=torch.float64), torch.ones(1, 1, dtype=torch.long), [4], [1])
     with pytest.raises(_lib.CtcB200Error):
         op(torch.zeros(1, 4, 5, device="cuda"), torch.ones(1, 1, dtype=torch.long), [4], [1], blank=7)
+
+
+def _raw_loss_grad(c, zero_infinity=True):
+    """One ctcb200_loss_grad call through the C ABI ('sum' reduction); returns nll, grad and the lattice
+    kernel's path counters [utterances in log space, of which: underflowed in the linear domain]."""
+    import ctypes
+    from asr_chinese_e2e_b200 import _lib
+    L = _lib.lib()
+    x = c["logits"].cuda()
+    tg, il, tl = c["targets"].cuda(), c["input_lengths"].cuda(), c["target_lengths"].cuda()
+    B, T, V = x.shape
+    U = tg.shape[1]
+    wsb = _lib.workspace_bytes(B, T, V, U)
+    ws = torch.zeros(wsb, dtype=torch.uint8, device="cuda")
+    nll = torch.empty(B, device="cuda"); sums = torch.zeros(4, device="cuda"); grad = torch.empty_like(x)
+    st = torch.cuda.current_stream().cuda_stream
+    rc = L.ctcb200_loss_grad(x.data_ptr(), tg.data_ptr(), U, tg.numel(), il.data_ptr(), tl.data_ptr(), B, T, V, U, 0,
+                             int(zero_infinity), 2, 1.0, nll.data_ptr(), sums.data_ptr(), grad.data_ptr(),
+                             ws.data_ptr(), wsb, st, None)
+    assert rc == 0, _lib.strerror(rc)
+    stats = (ctypes.c_int * 2)()
+    assert L.ctcb200_read_lattice_stats(ws.data_ptr(), stats, st) == 0
+    return nll.cpu().numpy(), grad.cpu().numpy(), list(stats)
+
+
+def _f64(c, zero_infinity=True):
+    _, n64, g64 = ctc_c_f64(*[c[k].numpy() for k in ("logits", "targets", "input_lengths", "target_lengths")],
+                            reduction="sum", zero_infinity=zero_infinity)
+    return n64, g64
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("umax", [12, 100, 200])
+def test_linear_domain_lattice_is_the_default_and_matches_float64(umax):
+    """Ordinary inputs run the linear-domain (float64, per-lane exponent) recursion for every utterance, for
+    all three lattice widths (4 / 8 / 16 states per lane), and agree with the float64 oracle far inside the
+    parity tolerances."""
+    c = make_case(5, 2 * umax + 37, 53, umax, 900 + umax, dist="D2")
+    nll, g, stats = _raw_loss_grad(c)
+    assert stats == [0, 0]
+    n64, g64 = _f64(c)
+    # (the fp32 rounding of the gathered log-probabilities themselves is ~5e-7 per frame)
+    assert (np.abs(nll - n64) <= 1e-6 * np.abs(n64) + 2e-5).all()
+    assert np.abs(g - g64).max() < 2e-5
+
+
+@pytest.mark.gpu
+def test_blank_dominated_posteriors_stay_on_the_linear_path():
+    """Early-training regime: the model predicts blank with probability ~1 and every label with ~2^-35, so
+    alpha spreads over ~2^-35 per label ACROSS the states of a frame (2^-1400 over 40 labels) -- beyond any
+    single warp-wide scale in float64; the per-lane exponents hold it."""
+    c = make_case(4, 120, 61, 40, 4242, dist="D1", full_targets=True)
+    c["logits"][:, :, 0] += 24.0
+    nll, g, stats = _raw_loss_grad(c)
+    assert stats == [0, 0]
+    n64, g64 = _f64(c)
+    assert np.isfinite(nll).all()
+    assert (np.abs(nll - n64) <= 1e-6 * np.abs(n64) + 2e-5).all()
+    assert np.abs(g - g64).max() < 2e-5
+
+
+@pytest.mark.gpu
+def test_out_of_range_and_infeasible_utterances_fall_back_to_log_space():
+    """Utterances with a gathered log-probability below the linear path's range (flagged by the sweep) and
+    utterances whose likelihood is zero run the log-space recursion; the rest of the batch stays linear."""
+    c = make_case(6, 60, 47, 9, 31337, dist="D1", n_infeasible=1)      # utterance 1 is infeasible
+    c["logits"][3] *= 60.0                                              # gaps of hundreds of nats
+    c["logits"][4, 7, int(c["targets"][4, 0])] = -400.0                # one gathered value far out of range
+    nll, g, stats = _raw_loss_grad(c)
+    assert stats == [3, 1], stats
+    n64, g64 = _f64(c)
+    assert nll[1] == 0.0 and not g[1].any()                            # zero_infinity
+    fin = np.isfinite(n64)
+    assert np.abs(nll[fin] - n64[fin]).max() / np.abs(n64[fin]).max() < 1e-5
+    assert np.abs(g - g64).max() < 1e-3
+    # the flags are per call: the same workspace shape on ordinary inputs is all-linear again
+    _, _, stats2 = _raw_loss_grad(make_case(6, 60, 47, 9, 31338, dist="D1"))
+    assert stats2 == [0, 0]
