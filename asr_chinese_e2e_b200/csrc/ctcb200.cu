@@ -102,7 +102,7 @@ struct K1Args {
     const float *logits; const int64_t *targets; int64_t tnumel; const int *Tb, *Ub; const int64_t *toff;
     const int *rowstart; float *lp_lab; int *hdr; int B, T, V, Lp, blank;
     float *grad; int reduction; float inv_batch;   // fused (2-sweep) mode only
-    int *best; int zero_pad_here; int *slow; float lin_thr; float *p_lab;
+    int *best; int zero_pad_here; int *slow; float lin_thr;
 };
 struct K3Args {
     const float *logits; const int64_t *targets; int64_t tnumel; const int *Tb, *Ub; const int64_t *toff;
@@ -117,7 +117,7 @@ cudaError_t launch_k1x(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
     if (e != cudaSuccess) return e;
     return launch_pdl(0, k1_lse_gather<NT, MAXC, EXACT, FUSED>, dim3(c.grid), dim3(NT), c.smem, s, a.logits, a.targets,
                       a.tnumel, a.Tb, a.Ub, a.toff, a.rowstart, a.lp_lab, a.hdr, a.B, a.T, a.V, a.Lp, a.blank, c.nst,
-                      c.slot_bytes, a.grad, a.reduction, a.inv_batch, a.best, a.zero_pad_here, a.slow, a.lin_thr, a.p_lab);
+                      c.slot_bytes, a.grad, a.reduction, a.inv_batch, a.best, a.zero_pad_here, a.slow, a.lin_thr);
 }
 template <int NT, int MAXC, bool EXACT>
 cudaError_t launch_k1(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
@@ -163,13 +163,13 @@ cudaError_t launch_k2(cudaStream_t s, const int64_t *targets, int64_t tnumel, co
                       const int64_t *toff, int *flags, const float *lp_lab, float *gam, float *ab, float *nll,
                       float *loss_sums, unsigned *ticket, int B, int T, int zero_inf, float *zero_grad,
                       const int *rowstart, int V, int zero_ctas, double *tile_off, float mean_scale, const int *slow,
-                      size_t ab_utt, const float *p_lab) {
+                      size_t ab_utt) {
     constexpr uint32_t smem = k2_smem_bytes<NS, GRAD>();
     cudaError_t e = cudaFuncSetAttribute(k2_lattice<NS, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return launch_pdl(1, k2_lattice<NS, GRAD>, dim3((B + 1) / 2 + (zero_grad ? zero_ctas : 0)), dim3(128), smem, s,
                       targets, tnumel, Tb, Ub, toff, flags, lp_lab, gam, ab, nll, loss_sums, ticket, B, T, zero_inf,
-                      zero_grad, rowstart, V, tile_off, mean_scale, slow, ab_utt, p_lab);
+                      zero_grad, rowstart, V, tile_off, mean_scale, slow, ab_utt);
 }
 
 struct FusedGrad {          // non-null grad => 2-sweep mode: the sweep writes g*softmax, k3p adds -g*occupancy
@@ -243,7 +243,7 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     {
         const K1Args a = {logits, targets, tnumel, Tb, Ub, toff, rowstart, lp_lab, hdr, B, T, V, g.Lp, blank,
                           fused ? fg->grad : nullptr, fused ? fg->reduction : 0, fused ? fg->inv_batch : 0.f,
-                          want_argmax ? (int *)(ws + w.best) : nullptr, zero_in_lattice ? 0 : 1, slow, lin_thr, (float *)(ws + w.p_lab)};
+                          want_argmax ? (int *)(ws + w.best) : nullptr, zero_in_lattice ? 0 : 1, slow, lin_thr};
         if (fused) {
             if (nt1 == 64) e = STREAM_DISPATCH(launch_k1f, 64, rounds1, exact1, c, s, a);
             else e = STREAM_DISPATCH(launch_k1f, 128, rounds1, exact1, c, s, a);
@@ -261,7 +261,7 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     unsigned *ticket = (unsigned *)(hdr + 1);
 #define K2_ARGS s, targets, tnumel, Tb, Ub, toff, flags, lp_lab, gam, ab, nll, loss_sums, ticket, B, T, zero_infinity, \
                 (zero_in_lattice ? fg->grad : nullptr), rowstart, V, dev.sms * env_int("CTCB200_ZERO_CPS", 2),   \
-                (double *)(ws + w.tile_off), (fused ? fg->inv_batch : 1.f / (float)B), slow, w.ab_utt, (const float *)(ws + w.p_lab)
+                (double *)(ws + w.tile_off), (fused ? fg->inv_batch : 1.f / (float)B), slow, w.ab_utt
     if (want_grad) {
         if (g.NS == 4) e = launch_k2<4, true>(K2_ARGS);
         else if (g.NS == 8) e = launch_k2<8, true>(K2_ARGS);

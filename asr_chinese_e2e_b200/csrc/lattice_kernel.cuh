@@ -118,6 +118,10 @@ __device__ __forceinline__ void lat_step(LatLane<NS> &L, uint32_t fa, int t, flo
     constexpr int NL = NS / 2;
     lpb = lds_f32(fa);
     lds_vec<NL>(lpl, fa + 16 + 4 * NL * L.lane);
+    // self-describing frame values (layout.h): v > 0 is a probability, otherwise already a log2-probability
+    lpb = lpb > 0.f ? lg2f(lpb) : lpb;
+#pragma unroll
+    for (int jj = 0; jj < NL; ++jj) lpl[jj] = lpl[jj] > 0.f ? lg2f(lpl[jj]) : lpl[jj];
     float nw[NS];
     if (DIR == 0) {
         if (t == 0) {

@@ -17,9 +17,9 @@
 // to 0, which includes the truly infeasible ones -- run the log-space recursion of lattice_kernel.cuh
 // instead, so the result is defined for every input.
 //
-// The emission probabilities come from the sweep kernel, which writes every gathered log2-probability a second
-// time as a float probability 2^lp (p_lab; representable because the linear path only runs when all of them
-// are >= 2^-90); a lane converts its NS/2+1 values of a frame to double (exact), off the dependent chain.
+// The emission probabilities come from the sweep kernel, which stores a gathered value as the float probability
+// 2^lp itself whenever it is in range (layout.h; representable because the linear path only runs when all of
+// them are >= 2^-90); a lane converts its NS/2+1 values of a frame to double (exact), off the dependent chain.
 // Relative error 2^-22 per factor, i.e. ~1e-9 relative on the log-likelihood -- far inside what an fp32
 // log-space recursion gives.
 //
@@ -108,9 +108,11 @@ __device__ __forceinline__ void lin_load_p(LinP<NS> &P, uint32_t fa, int lane) {
     float pl[NL];
     const float pb = lds_f32(fa);
     lds_vec<NL>(pl, fa + 16 + 4 * NL * lane);
-    P.pb = (double)pb;                                           // exact; the sweep wrote 2^lp as a float (>= 2^-90 here)
+    // exact conversions: the sweep stored 2^lp as a float (>= 2^-90 on this path); the only non-positive values
+    // here are the sentinels of unused label slots -> probability 0
+    P.pb = (double)fmaxf(pb, 0.f);
 #pragma unroll
-    for (int jj = 0; jj < NL; ++jj) P.pl[jj] = (double)pl[jj];
+    for (int jj = 0; jj < NL; ++jj) P.pl[jj] = (double)fmaxf(pl[jj], 0.f);
 }
 
 // One recursion step.  INIT: the first step of the direction (t = 0 for alpha, t = T_b - 1 for beta).
@@ -176,7 +178,7 @@ template <int NS, bool GRAD, int DIR>
 __device__ __forceinline__ bool lattice_lin_dir(uint32_t ring, uint32_t bar0, uint32_t xch, uint32_t bx, int bar_id,
                                                 int lane, int b, int Tb, int Ub,
                                                 const int64_t *__restrict__ targets, int64_t tnumel, int64_t toff,
-                                                int *__restrict__ flags, const float *__restrict__ p_lab,
+                                                int *__restrict__ flags, const float *__restrict__ lp_lab,
                                                 float *__restrict__ gam, unsigned char *__restrict__ ab_utt,
                                                 float *__restrict__ nll, int T) {
     using C = LinCfg<NS, GRAD>;
@@ -257,7 +259,7 @@ __device__ __forceinline__ bool lattice_lin_dir(uint32_t ring, uint32_t bar0, ui
     const int Qm = Tm / TT;
     const int n1 = DIR ? (Qtot - Qm) : Qm;
     const int ntot = GRAD ? Qtot : (DIR ? n1 : Qm + 1);
-    const float *lp_base = p_lab + (size_t)b * T * Lp;            // frames of probabilities
+    const float *lp_base = lp_lab + (size_t)b * T * Lp;           // on this path every blank/label value is a probability
     float *gam_base = gam + (size_t)b * T * Lp;
     int nact = (2 * Ub + 1 + NS - 1) / NS;                       // lanes that hold a real state
     nact = nact > 32 ? 32 : nact;
@@ -463,8 +465,7 @@ k2_lattice(const int64_t *__restrict__ targets, int64_t tnumel, const int *__res
            const float *__restrict__ lp_lab, float *__restrict__ gam, float *__restrict__ ab_ws,
            float *__restrict__ nll, float *__restrict__ loss_sums, unsigned *__restrict__ ticket, int B,
            int T, int zero_inf, float *__restrict__ zero_grad, const int *__restrict__ rowstart, int V,
-           double *__restrict__ tile_off, float mean_scale, const int *__restrict__ slow, size_t ab_utt_bytes,
-           const float *__restrict__ p_lab) {
+           double *__restrict__ tile_off, float mean_scale, const int *__restrict__ slow, size_t ab_utt_bytes) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     griddep_wait();                                              // the sweep's lp_lab frames
@@ -496,9 +497,9 @@ k2_lattice(const int64_t *__restrict__ targets, int64_t tnumel, const int *__res
         bool done = false;
         if (!slow[b]) {
             done = dir == 0 ? lattice_lin_dir<NS, GRAD, 0>(ring, bars_lin, xch, bx, 1 + pair, lane, b, Tb, Ub, targets,
-                                                           tnumel, toff, flags, p_lab, gam, ab_utt, nll, T)
+                                                           tnumel, toff, flags, lp_lab, gam, ab_utt, nll, T)
                             : lattice_lin_dir<NS, GRAD, 1>(ring, bars_lin, xch, bx, 1 + pair, lane, b, Tb, Ub, targets,
-                                                           tnumel, toff, flags, p_lab, gam, ab_utt, nll, T);
+                                                           tnumel, toff, flags, lp_lab, gam, ab_utt, nll, T);
             if (!done) {
                 named_bar_sync(1 + pair, 64);                    // both warps are out of the rings and of xch
                 if (dir == 0 && lane == 0) atomicAdd(ticket + 2, 1u);   // debug counter: underflowed / infeasible

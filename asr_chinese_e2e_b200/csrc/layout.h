@@ -26,8 +26,11 @@ static inline bool geom_for(int Umax, Geom *g) {
     return true;
 }
 
-// Frame layout (floats), log2 units:  [0] blank, [1] lse2 of the frame, [2..3] unused,
-// [4+j] label slot j (j < U_b; the finite log(0) sentinel -1e30 beyond).  In `gam` the same slots hold the posterior
+// Frame layout (floats):  [0] blank, [1] lse2 of the frame (log2 units), [2..3] unused, [4+j] label slot j
+// (j < U_b; the finite log(0) sentinel -1e30 beyond).  A blank/label value is SELF-DESCRIBING: v > 0 is the
+// probability 2^lp itself (what the linear-domain lattice multiplies by; written whenever lp >= the path's range
+// limit, i.e. p >= 2^-90), v <= 0 (or NaN) is the log2-probability lp (out-of-range values, the sentinel).  The
+// log-space lattice decodes v > 0 with one lg2.  In `gam` the same slots hold the posterior
 // state occupancies: [0] sum over all blank states, [4+j] label state of slot j.
 
 // Frames per stage of the linear-domain lattice (also its renormalisation interval).
@@ -55,7 +58,6 @@ struct Workspace {
     size_t toff;      // int64[B] element offset of utterance b's labels in `targets`
     size_t rowstart;  // int[B+1] exclusive prefix sum of Tb (valid-frame numbering)
     size_t lp_lab;    // float[B*T*Lp]
-    size_t p_lab;     // float[B*T*Lp]  the same frames as probabilities 2^lp (slot [1] again lse2): linear-domain lattice
     size_t gam;       // float[B*T*Lp]
     size_t ab;        // stored alpha/beta halves: B blocks of ab_utt bytes (see lin_ab_utt_bytes)
     size_t ab_utt;    // bytes per utterance of `ab`
@@ -76,7 +78,6 @@ static inline Workspace workspace_layout(int B, int T, const Geom &g) {
     w.toff = o;      o += align_up(sizeof(int64_t) * b);
     w.rowstart = o;  o += align_up(sizeof(int) * (b + 1));
     w.lp_lab = o;    o += align_up(sizeof(float) * b * T * g.Lp);
-    w.p_lab = o;     o += align_up(sizeof(float) * b * T * g.Lp);
     w.gam = o;       o += align_up(sizeof(float) * b * T * g.Lp);
     w.ab_utt = lin_ab_utt_bytes(T, g);
     w.ab = o;        o += align_up(w.ab_utt * b);

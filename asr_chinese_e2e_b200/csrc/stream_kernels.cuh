@@ -203,8 +203,7 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
               const int64_t *__restrict__ toff_arr, const int *__restrict__ rowstart,
               float *__restrict__ lp_lab, int *__restrict__ hdr, int B, int T, int V, int Lp, int blank,
               int nst, uint32_t slot_bytes, float *__restrict__ grad, int reduction, float inv_batch,
-              int *__restrict__ best, int zero_pad_here, int *__restrict__ slow, float lin_thr,
-              float *__restrict__ p_lab) {
+              int *__restrict__ best, int zero_pad_here, int *__restrict__ slow, float lin_thr) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     griddep_wait();                                  // k0_prep's lengths / prefix sums
@@ -365,22 +364,22 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
             best[(size_t)cc.b * T + cc.t] = NT == 128 ? min(min(ri[0], ri[1]), min(ri[2], ri[3])) : min(ri[0], ri[1]);
         }
         float *frame = lp_lab + ((size_t)cc.b * T + cc.t) * Lp;
-        float *pframe = p_lab + ((size_t)cc.b * T + cc.t) * Lp;
 #pragma unroll
         for (int kk = 0; kk < MAXG; ++kk) {
             const int k = tid + kk * NT;
             if (k < Lp) {
-                float o, pr;
+                float o;
                 if (cg[kk] >= 0) {
-                    o = fmaxf(fmaf(xg[kk], kLog2e, -lse2), kNeg);   // -inf logit -> sentinel
-                    pr = ex2f(o);
-                    if (!(o >= lin_thr)) slow[cc.b] = 1;            // (or NaN) outside the linear-domain lattice's range
+                    // log2-probability, <= 0 (-inf logit -> the finite sentinel).  In range of the linear-domain
+                    // lattice it is stored as the probability itself (> 0); otherwise as is, and the utterance is
+                    // flagged for the log-space recursion (layout.h: self-describing frame values)
+                    o = fminf(fmaxf(fmaf(xg[kk], kLog2e, -lse2), kNeg), 0.f);
+                    if (o >= lin_thr) o = ex2f(o);
+                    else slow[cc.b] = 1;                           // (also NaN)
                 } else {
                     o = cg[kk] == -2 ? lse2 : (cg[kk] == -3 ? 0.f : kNeg);
-                    pr = cg[kk] == -2 ? lse2 : 0.f;
                 }
                 stg_f32_hint(frame + k, o, kEvictLast);           // re-read by the lattice kernel
-                stg_f32_hint(pframe + k, pr, kEvictLast);
             }
         }
         if (FUSED) {

@@ -34,10 +34,10 @@ def test_header_symbols_exported(lib):
 
 
 def test_workspace_bytes_is_host_arithmetic(lib):
-    # frames of 4+16*NS floats (NS=4 up to U=63) for lp_lab, p_lab and gam, stored half-lattice stages of
+    # frames of 4+16*NS floats (NS=4 up to U=63) for lp_lab and gam, stored half-lattice stages of
     # {32 lane exponents, 8 rows of 32*NS doubles}, 1 int argmax per frame, 1 double per 8 frames
     b = _lib.workspace_bytes(256, 400, 4234, 50)
-    want = 256 * 400 * (3 * 68 + 1) * 4 + 256 * 50 * (128 + 8 * 128 * 8) + 256 * 50 * 8
+    want = 256 * 400 * (2 * 68 + 1) * 4 + 256 * 50 * (128 + 8 * 128 * 8) + 256 * 50 * 8
     assert want <= b <= want + 64 * 1024
     assert _lib.workspace_bytes(64, 1500, 4234, 120) > 64 * 1500 * (2 * 132 + 256) * 4
     out = ctypes.c_size_t(0)
