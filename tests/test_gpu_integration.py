@@ -211,3 +211,19 @@ def test_greedy_decode_and_edit_distance_on_device():
     ctc_loss_b200(xg, c["targets"].cuda(), c["input_lengths"].cuda(), c["target_lengths"].cuda(), zero_infinity=True,
                   decode=info2).backward()
     assert torch.equal(info2["edit_distance"], info["edit_distance"]) and torch.equal(info2["hyp"], info["hyp"])
+
+
+def test_masks_on_the_device_match_the_reference_loop():
+    """Section 8(f) row 4: length masks built on the GPU from GPU-resident lengths (one broadcast compare, no
+    host loop, nothing read back) equal the reference's per-utterance slice assignments."""
+    from asr_chinese_e2e_b200 import get_attn_pad_mask, get_non_pad_mask
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(64, 400, 8, generator=g).cuda()
+    lens = torch.randint(200, 401, (64,), generator=g)
+    want = x.new_ones(64, 400)
+    for i in range(64):                                              # reference utils.py:106-108
+        want[i, int(lens[i]):] = 0
+    got = get_non_pad_mask(x, input_lengths=lens.cuda())
+    assert got.is_cuda and torch.equal(got.squeeze(-1), want)
+    att = get_attn_pad_mask(x, lens.cuda(), 5)
+    assert att.shape == (64, 5, 400) and torch.equal(att[:, 0], want.lt(1))
