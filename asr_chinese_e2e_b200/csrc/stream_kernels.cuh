@@ -633,30 +633,27 @@ k3p_patch(const int64_t *__restrict__ targets, int64_t tnumel, const int *__rest
                 if (!first[kk]) continue;
                 const int k = tid + kk * NT;
                 float *gp = gbase + mycls[kk];
-                const bool single = pnext[k] < 0;           // the common case: the class occurs once
                 const int off = k == 0 ? 0 : 3 + k;
-                int r = 0;
-                if (single) {                               // 16 frames in flight per thread (independent loads)
-                    for (; r + 16 <= seg; r += 16) {
-                        float o[16];
+                // 16 frames in flight per thread (independent loads), ragged tail included; a class that occurs
+                // several times in the utterance adds the occupancies of its other slots, 16 frames at a time too
+                for (int r = 0; r < seg; r += 16) {
+                    float o[16];
 #pragma unroll
-                        for (int u = 0; u < 16; ++u) o[u] = __ldg(gf + (size_t)(r + u) * Lp + off);
+                    for (int u = 0; u < 16; ++u) o[u] = r + u < seg ? __ldg(gf + (size_t)(r + u) * Lp + off) : 0.f;
+                    for (int j = pnext[k]; j >= 0; j = pnext[j]) {
 #pragma unroll
                         for (int u = 0; u < 16; ++u)
-                            if (o[u] != 0.f) {
-#ifdef CTCB200_EXPERIMENT_PLAIN_STORE
-                                gp[(size_t)(r + u) * V] = ng * o[u];      // timing experiment only (wrong values)
-#else
-                                atomicAdd(gp + (size_t)(r + u) * V, ng * o[u]);   // RED: no return value
-#endif
-                            }
+                            if (r + u < seg) o[u] += __ldg(gf + (size_t)(r + u) * Lp + 3 + j);
                     }
-                }
-                for (; r < seg; ++r) {
-                    const float *f = gf + (size_t)r * Lp;
-                    float occ = 0.f;
-                    for (int j = k; j >= 0; j = pnext[j]) occ += (j == 0 ? f[0] : f[3 + j]);
-                    if (occ != 0.f) atomicAdd(gp + (size_t)r * V, ng * occ);
+#pragma unroll
+                    for (int u = 0; u < 16; ++u)
+                        if (o[u] != 0.f) {
+#ifdef CTCB200_EXPERIMENT_PLAIN_STORE
+                            gp[(size_t)(r + u) * V] = ng * o[u];          // timing experiment only (wrong values)
+#else
+                            atomicAdd(gp + (size_t)(r + u) * V, ng * o[u]);   // RED: no return value
+#endif
+                        }
                 }
             }
         }
