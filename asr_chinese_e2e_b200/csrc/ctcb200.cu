@@ -22,7 +22,9 @@ int env_int(const char *name, int dflt) {
     const char *s = getenv(name);
     return (s && *s) ? atoi(s) : dflt;
 }
-const int g_use_pdl = env_int("CTCB200_PDL", 0);   // bit 0: sweep after prep, bit 1: lattice after sweep, bit 2: patch after lattice
+// bit 0: sweep after prep (measured: +70 us per step in a back-to-back loop), bit 1: lattice after sweep,
+// bit 2: patch after lattice (its class tables are built while the lattice drains: -5 us)
+const int g_use_pdl = env_int("CTCB200_PDL", 6);
 
 struct DevInfo {
     int sms;
@@ -89,11 +91,12 @@ int stream_cfg(int V, uint32_t stage_extra, size_t fixed_extra, int sms, int dfl
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(int edge, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                        Args... args) {
+    // edge < 0: plain launch (the previous operation on the stream is not the producer kernel of this call)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = (g_use_pdl >> edge) & 1;
+    attr[0].val.programmaticStreamSerializationAllowed = edge >= 0 ? (g_use_pdl >> edge) & 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
@@ -163,11 +166,11 @@ cudaError_t launch_k2(cudaStream_t s, const int64_t *targets, int64_t tnumel, co
                       const int64_t *toff, int *flags, const float *lp_lab, float *gam, float *ab, float *nll,
                       float *loss_sums, unsigned *ticket, int B, int T, int zero_inf, float *zero_grad,
                       const int *rowstart, int V, int zero_ctas, double *tile_off, float mean_scale, const int *slow,
-                      size_t ab_utt) {
+                      size_t ab_utt, bool follows_sweep) {
     constexpr uint32_t smem = k2_smem_bytes<NS, GRAD>();
     cudaError_t e = cudaFuncSetAttribute(k2_lattice<NS, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return launch_pdl(1, k2_lattice<NS, GRAD>, dim3((B + 1) / 2 + (zero_grad ? zero_ctas : 0)), dim3(128), smem, s,
+    return launch_pdl(follows_sweep ? 1 : -1, k2_lattice<NS, GRAD>, dim3((B + 1) / 2 + (zero_grad ? zero_ctas : 0)), dim3(128), smem, s,
                       targets, tnumel, Tb, Ub, toff, flags, lp_lab, gam, ab, nll, loss_sums, ticket, B, T, zero_inf,
                       zero_grad, rowstart, V, tile_off, mean_scale, slow, ab_utt);
 }
@@ -261,7 +264,7 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     unsigned *ticket = (unsigned *)(hdr + 1);
 #define K2_ARGS s, targets, tnumel, Tb, Ub, toff, flags, lp_lab, gam, ab, nll, loss_sums, ticket, B, T, zero_infinity, \
                 (zero_in_lattice ? fg->grad : nullptr), rowstart, V, dev.sms * env_int("CTCB200_ZERO_CPS", 2),   \
-                (double *)(ws + w.tile_off), (fused ? fg->inv_batch : 1.f / (float)B), slow, w.ab_utt
+                (double *)(ws + w.tile_off), (fused ? fg->inv_batch : 1.f / (float)B), slow, w.ab_utt, ((stages & 1) && !sweep_done)
     if (want_grad) {
         if (g.NS == 4) e = launch_k2<4, true>(K2_ARGS);
         else if (g.NS == 8) e = launch_k2<8, true>(K2_ARGS);
@@ -278,7 +281,7 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
         const int per = env_int("CTCB200_K3P_CPS", 32);
         const size_t smem = 2 * (size_t)g.Lp * 4;
         prefer_max_carveout(k3p_patch<64>);
-        e = launch_pdl(2, k3p_patch<64>, dim3(dev.sms * (per < 1 ? 1 : per)), dim3(64), smem, s, targets, tnumel, Tb, Ub, toff,
+        e = launch_pdl((stages & 2) ? 2 : -1, k3p_patch<64>, dim3(dev.sms * (per < 1 ? 1 : per)), dim3(64), smem, s, targets, tnumel, Tb, Ub, toff,
                        flags, rowstart, gam, fg->grad, fg->reduction, fg->inv_batch, B, T, V, g.Lp, blank, zero_infinity);
     }
     return (int)e;

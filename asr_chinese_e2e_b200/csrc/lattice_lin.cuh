@@ -495,7 +495,7 @@ k2_lattice(const int64_t *__restrict__ targets, int64_t tnumel, const int *__res
         const uint32_t xch = sb + M::OFF_XCH + pair * 32, bx = sb + M::OFF_BX + pair * M::BX;
         const uint32_t bars_lin = sb + M::OFF_BARS_LIN + wq * M::NSTG * 8, bars_log = sb + M::OFF_BARS_LOG + wq * M::NSTG * 8;
         bool done = false;
-        if (!slow[b]) {
+        if (!__ldcg(slow + b)) {                                 // (written by the sweep: coherent load, see k3p_patch)
             done = dir == 0 ? lattice_lin_dir<NS, GRAD, 0>(ring, bars_lin, xch, bx, 1 + pair, lane, b, Tb, Ub, targets,
                                                            tnumel, toff, flags, lp_lab, gam, ab_utt, nll, T)
                             : lattice_lin_dir<NS, GRAD, 1>(ring, bars_lin, xch, bx, 1 + pair, lane, b, Tb, Ub, targets,

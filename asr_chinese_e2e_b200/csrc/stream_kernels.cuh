@@ -580,7 +580,10 @@ k3p_patch(const int64_t *__restrict__ targets, int64_t tnumel, const int *__rest
     int *pcls = (int *)smem;                  // [Lp] class of patch slot k (0 = blank, k>=1: label k-1)
     int *pnext = pcls + Lp;                   // [Lp] next slot with the same class, or -1
     const int tid = threadIdx.x;
-    griddep_wait();                           // the lattice's occupancies, the sweep's dense gradient
+    // Launched with programmatic stream serialization this kernel may start while the lattice kernel is still
+    // running: everything up to griddep_wait() below reads only the call's inputs and k0_prep's arrays (complete
+    // before the lattice kernel itself could start), so the class tables of the first segment are built early.
+    bool waited = false;
     int r0, nrows;
     grid_share(rowstart[B], r0, nrows);
     if (nrows <= 0) return;
@@ -592,40 +595,42 @@ k3p_patch(const int64_t *__restrict__ targets, int64_t tnumel, const int *__rest
         const int b = cc.b, t0 = cc.t;
         const int seg = (cc.Tb - t0) < (nrows - i) ? (cc.Tb - t0) : (nrows - i);
         const int Ub = Ub_arr[b];
-        const int infeasible = flags[b];
         float *gbase = grad + ((size_t)b * T + t0) * V;
-        if (infeasible) {
+        const float g = reduction == 1 ? inv_batch * __frcp_rn((float)(Ub > 1 ? Ub : 1)) : 1.f;
+        const int64_t toff = toff_arr[b];
+        __syncthreads();                       // previous segment's table reads are done
+        for (int k = tid; k <= Ub; k += NT) {
+            long long c = blank;
+            if (k > 0) {
+                const int64_t idx = toff + (k - 1);
+                c = idx < tnumel ? targets[idx] : 0;
+                c = c < 0 ? 0 : (c >= V ? V - 1 : c);
+            }
+            pcls[k] = (int)c;
+        }
+        __syncthreads();
+        int mycls[MAXP];
+        bool first[MAXP];
+#pragma unroll
+        for (int kk = 0; kk < MAXP; ++kk) {
+            const int k = tid + kk * NT;
+            mycls[kk] = -1; first[kk] = false;
+            if (k <= Ub) {
+                const int c = pcls[k];
+                int f = 1, nx = -1;
+                for (int j = 0; j < k; ++j) if (pcls[j] == c) { f = 0; break; }
+                for (int j = k + 1; j <= Ub; ++j) if (pcls[j] == c) { nx = j; break; }
+                pnext[k] = nx; mycls[kk] = c; first[kk] = f;
+            }
+        }
+        __syncthreads();
+        if (!waited) { griddep_wait(); waited = true; }   // the lattice's occupancies and flags, the sweep's dense gradient
+        // (coherent L2 loads for everything the lattice kernel wrote: this kernel may have started, and the SM's
+        // non-coherent cache may have been primed, before those writes)
+        if (__ldcg(flags + b)) {               // no valid alignment
             if (zero_inf) zero_span<NT>(gbase, (size_t)seg * V, tid);
             else fill_span<NT>(gbase, (size_t)seg * V, tid, __int_as_float(0x7fc00000));
         } else {
-            const float g = reduction == 1 ? inv_batch * __frcp_rn((float)(Ub > 1 ? Ub : 1)) : 1.f;
-            const int64_t toff = toff_arr[b];
-            __syncthreads();                   // previous segment's table reads are done
-            for (int k = tid; k <= Ub; k += NT) {
-                long long c = blank;
-                if (k > 0) {
-                    const int64_t idx = toff + (k - 1);
-                    c = idx < tnumel ? targets[idx] : 0;
-                    c = c < 0 ? 0 : (c >= V ? V - 1 : c);
-                }
-                pcls[k] = (int)c;
-            }
-            __syncthreads();
-            int mycls[MAXP];
-            bool first[MAXP];
-#pragma unroll
-            for (int kk = 0; kk < MAXP; ++kk) {
-                const int k = tid + kk * NT;
-                mycls[kk] = -1; first[kk] = false;
-                if (k <= Ub) {
-                    const int c = pcls[k];
-                    int f = 1, nx = -1;
-                    for (int j = 0; j < k; ++j) if (pcls[j] == c) { f = 0; break; }
-                    for (int j = k + 1; j <= Ub; ++j) if (pcls[j] == c) { nx = j; break; }
-                    pnext[k] = nx; mycls[kk] = c; first[kk] = f;
-                }
-            }
-            __syncthreads();
             const float *gf = gam + ((size_t)b * T + t0) * Lp;
             const float ng = -g;
 #pragma unroll
@@ -639,11 +644,11 @@ k3p_patch(const int64_t *__restrict__ targets, int64_t tnumel, const int *__rest
                 for (int r = 0; r < seg; r += 16) {
                     float o[16];
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) o[u] = r + u < seg ? __ldg(gf + (size_t)(r + u) * Lp + off) : 0.f;
+                    for (int u = 0; u < 16; ++u) o[u] = r + u < seg ? __ldcg(gf + (size_t)(r + u) * Lp + off) : 0.f;
                     for (int j = pnext[k]; j >= 0; j = pnext[j]) {
 #pragma unroll
                         for (int u = 0; u < 16; ++u)
-                            if (r + u < seg) o[u] += __ldg(gf + (size_t)(r + u) * Lp + 3 + j);
+                            if (r + u < seg) o[u] += __ldcg(gf + (size_t)(r + u) * Lp + 3 + j);
                     }
 #pragma unroll
                     for (int u = 0; u < 16; ++u)
