@@ -133,7 +133,7 @@ def _decode_chunks(L, decode, tg, stride, chunks, T, V, umax, blank, stream, dev
 
 
 def _two_sweep_pipeline(ctx, L, x, tg, stride, il, tl, B, T, V, umax, blank, zi, red, inv_b, nll, grad, reduction,
-                        decode=None):
+                        decode=None, lattice_event=None):
     """Default training path.  Two utterance chunks (80 % / 20 %):
 
         main stream:  sweep(a)  sweep(b)            patch(a)   patch(b)
@@ -163,7 +163,14 @@ def _two_sweep_pipeline(ctx, L, x, tg, stride, il, tl, B, T, V, umax, blank, zi,
 
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream()
-        if n_ch == 1:
+        if n_ch == 1 and lattice_event is not None:
+            # the loss value is final after the lattice: let the caller start its collective on it while the
+            # sparse patch of the gradient still runs (sharded.py)
+            call(0, 3, main)
+            lattice_event[0].record(main)
+            lattice_event[1] = True
+            call(0, 4, main)
+        elif n_ch == 1:
             call(0, 7, main)
         else:
             side = _side_streams(dev)[0]
@@ -203,7 +210,7 @@ class _CTCLossB200Fn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, logits, targets, input_lengths, target_lengths, blank, reduction, zero_infinity,
-                inv_batch, max_target_length, fused, chunks, decode):
+                inv_batch, max_target_length, fused, chunks, decode, lattice_event=None):
         x, tg, stride, il, tl, B, T, V, umax = _prepare(logits, targets, input_lengths, target_lengths,
                                                         blank, max_target_length)
         L = _lib.lib()
@@ -218,7 +225,7 @@ class _CTCLossB200Fn(torch.autograd.Function):
         grad = torch.empty_like(x) if fused else None
         if fused and two_sweep and chunks is None and "CTCB200_CHUNKS" not in os.environ:
             out = _two_sweep_pipeline(ctx, L, x, tg, stride, il, tl, B, T, V, umax, int(blank), zi, red, inv_b,
-                                      nll, grad, reduction, decode)
+                                      nll, grad, reduction, decode, lattice_event)
             return out
         n_ch = _n_chunks(B, chunks)
         per = (B + n_ch - 1) // n_ch if B else 0
@@ -312,7 +319,7 @@ class _CTCLossB200Fn(torch.autograd.Function):
                                                   ctx.applied.data_ptr(), applied_new.data_ptr(), B, T, V, stream),
                            "ctcb200_rescale_grad")
                 ctx.applied = applied_new
-            return (grad,) + (None,) * 11
+            return (grad,) + (None,) * 12
         x, tg, ws = ctx.saved_tensors
         grad = torch.empty_like(x)
         xs = x.element_size() * T * V
@@ -329,12 +336,12 @@ class _CTCLossB200Fn(torch.autograd.Function):
                                               go.data_ptr() + lo * gs, 1 if red == 0 else 0, red, inv_b, n, T, V,
                                               umax, blank, zi, grad.data_ptr() + lo * xs,
                                               ws.data_ptr() + c * ws_bytes, ws_bytes, stream), "ctcb200_backward")
-        return (grad,) + (None,) * 11
+        return (grad,) + (None,) * 12
 
 
 def ctc_loss_b200(logits, targets, input_lengths, target_lengths, blank: int = 0,
                   reduction: str = "mean", zero_infinity: bool = False, *, inv_batch=None,
-                  max_target_length=None, fused=None, chunks=None, decode=None):
+                  max_target_length=None, fused=None, chunks=None, decode=None, lattice_event=None):
     """CTC loss on batch-major logits; same flags and results as ``F.ctc_loss`` (see module doc).
 
     inv_batch: 1/(global batch) for 'mean' when the batch is sharded over ranks (default 1/B).
@@ -345,6 +352,9 @@ def ctc_loss_b200(logits, targets, input_lengths, target_lengths, blank: int = 0
         is the default when the logits require grad (env CTCB200_FUSED=0 to disable); costs one
         extra [B,T,V] buffer held until backward, like autograd's own saved log-probs would.
     chunks: utterance chunks of the two-stream pipeline (default env CTCB200_CHUNKS or 1).
+    lattice_event: optional ``torch.cuda.Event``; recorded on the current stream as soon as the loss VALUE is final
+        (after the lattice kernel, before the sparse gradient patch), so a caller can overlap work that needs only
+        the value -- the all-reduce of ``sharded_ctc_loss`` -- with the rest of the call.
     decode: optional dict; if given it is filled with the on-device greedy (best-path) decode of the same
         forward pass -- ``edit_distance`` int32[B] (token-level Levenshtein distance to the targets),
         ``hyp_len`` int32[B], ``hyp`` int64[B,T] (blank-padded; skip with ``decode={"want_hyp": False}``).
@@ -355,8 +365,12 @@ def ctc_loss_b200(logits, targets, input_lengths, target_lengths, blank: int = 0
         fused = bool(int(os.environ.get("CTCB200_FUSED", "1")))
     if torch.is_tensor(targets) and targets.dim() == 1:
         chunks = 1
-    return _CTCLossB200Fn.apply(logits, targets, input_lengths, target_lengths, blank, reduction,
-                                zero_infinity, inv_batch, max_target_length, fused, chunks, decode)
+    ev = [lattice_event, False] if lattice_event is not None else None
+    out = _CTCLossB200Fn.apply(logits, targets, input_lengths, target_lengths, blank, reduction,
+                               zero_infinity, inv_batch, max_target_length, fused, chunks, decode, ev)
+    if ev is not None and not ev[1]:
+        lattice_event.record(torch.cuda.current_stream(out.device))   # paths that do not split the call
+    return out
 
 
 def ctc_greedy_cer_b200(logits, targets, input_lengths, target_lengths, blank: int = 0):

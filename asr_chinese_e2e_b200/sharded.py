@@ -7,7 +7,9 @@ collective.  The only exchange is ONE all-reduce of the 2-element buffer
 d loss / d logits_local = 1 / (B_global * U_b) * (softmax - occupancy), which is what a DDP
 all-reduce of parameter gradients (sum) then expects.  With equal shards (the reference's
 drop_last=True) 1/B_global is known before the kernels run, so the op's upstream gradient is exactly 1
-and nothing waits on the collective; nothing ever syncs with the host.
+and nothing waits on the collective; nothing ever syncs with the host.  The loss value is final after the
+lattice kernel, so the all-reduce is issued on a side stream behind an event recorded there and runs under
+the sparse gradient patch that follows on the main stream.
 
 The reference has no multi-process path at all (its only multi-GPU construct is a disabled
 nn.DataParallel wrapper, Predictor/Bases/base_model.py:9-21, main.py:80).
@@ -32,15 +34,38 @@ def combine_sharded_mean(local_sum: torch.Tensor, local_count: int, group=None) 
     return local + (buf[0] * inv - local.detach())            # value: global mean
 
 
-def combine_equal_shards(local_contrib: torch.Tensor, group=None) -> torch.Tensor:
+_SIDE = {}
+
+
+def _collective_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(dev, priority=-1)
+    return _SIDE[key]
+
+
+def combine_equal_shards(local_contrib: torch.Tensor, group=None, ready_event=None) -> torch.Tensor:
     """Equal shard sizes (drop_last=True, as the reference's loader: data/data_loader/ai_shell_1.py:103):
     local_contrib = sum_b nll_b/U_b / B_global is already this rank's share of the global mean, so the
     upstream gradient of the op stays exactly 1 (no rescale sweep) and the collective is one all-reduce
     of a single float, enqueued behind the kernels with no host sync."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local_contrib
-    tot = local_contrib.detach().clone()
-    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    if ready_event is not None and local_contrib.is_cuda:
+        # The value is final at `ready_event` (after the lattice kernel) while the current stream still has the
+        # sparse gradient patch queued: run the all-reduce on a side stream behind that event, so that its
+        # latency (tens of microseconds for one float over NVLink) hides under the patch kernel.
+        main = torch.cuda.current_stream(local_contrib.device)
+        side = _collective_stream(local_contrib.device)
+        side.wait_event(ready_event)
+        with torch.cuda.stream(side):
+            tot = local_contrib.detach().clone()
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+        tot.record_stream(main)
+        main.wait_stream(side)
+    else:
+        tot = local_contrib.detach().clone()
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
     return local_contrib + (tot - local_contrib.detach())     # value: global mean; gradient: d/d local = 1
 
 
@@ -51,10 +76,11 @@ def sharded_ctc_loss(logits, targets, input_lengths, target_lengths, blank: int 
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     B = logits.shape[0]
     if equal_shards:
+        ev = torch.cuda.Event() if (world > 1 and logits.is_cuda) else None
         local = ctc_loss_b200(logits, targets, input_lengths, target_lengths, blank=blank, reduction="mean",
                               zero_infinity=zero_infinity, inv_batch=1.0 / max(world * B, 1),
-                              max_target_length=max_target_length)
-        return combine_equal_shards(local, group)
+                              max_target_length=max_target_length, lattice_event=ev)
+        return combine_equal_shards(local, group, ready_event=ev)
     local_sum = ctc_loss_b200(logits, targets, input_lengths, target_lengths, blank=blank,
                               reduction="mean", zero_infinity=zero_infinity, inv_batch=1.0,
                               max_target_length=max_target_length)

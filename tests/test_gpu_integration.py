@@ -227,3 +227,26 @@ def test_masks_on_the_device_match_the_reference_loop():
     assert got.is_cuda and torch.equal(got.squeeze(-1), want)
     att = get_attn_pad_mask(x, lens.cuda(), 5)
     assert att.shape == (64, 5, 400) and torch.equal(att[:, 0], want.lt(1))
+
+
+def test_lattice_event_splits_the_call_without_changing_results():
+    """`lattice_event` (used by sharded_ctc_loss to start its all-reduce under the gradient patch) is recorded
+    once the loss value is final; loss and gradient are bit-identical to the single-call path."""
+    from asr_chinese_e2e_b200 import ctc_loss_b200
+    c = make_case(20, 60, 97, 9, 2024, n_infeasible=1)
+    args = [c[k].cuda() for k in ("targets", "input_lengths", "target_lengths")]
+    outs = []
+    for ev in (None, torch.cuda.Event()):
+        x = c["logits"].cuda().requires_grad_(True)
+        loss = ctc_loss_b200(x, *args, reduction="mean", zero_infinity=True, lattice_event=ev)
+        if ev is not None:
+            ev.synchronize()                                   # recorded (would raise / hang otherwise)
+            seen_early = loss.item()                           # the value is final at the event
+        loss.backward()
+        outs.append((loss.detach().clone(), x.grad.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert seen_early == outs[1][0].item()
+    with torch.no_grad():                                      # paths that do not split still record the event
+        ev = torch.cuda.Event()
+        ctc_loss_b200(c["logits"].cuda(), *args, reduction="mean", zero_infinity=True, lattice_event=ev)
+        ev.synchronize()
