@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(_HERE, "libctcb200.so")
 SOURCES = ["ctcb200.cu"]
-HEADERS = ["ptx.cuh", "layout.h", "stream_kernels.cuh", "lattice_kernel.cuh", "ce_kernel.cuh", "decode_kernel.cuh",
+HEADERS = ["ptx.cuh", "layout.h", "stream_kernels.cuh", "lattice_kernel.cuh", "lattice_lin.cuh", "ce_kernel.cuh", "decode_kernel.cuh",
            os.path.join("..", "..", "include", "ctcb200.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

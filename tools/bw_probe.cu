@@ -126,8 +126,8 @@ int main(int argc, char **argv) {
             size_t smem = (size_t)nst * slot + 8 * nst;
             if (smem * cps > 225 * 1024) continue;
             cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            for (int mode = 0; mode < 1; ++mode) {
-                int R = 8;
+            for (int mode = 0; mode < 3; ++mode) {
+                int R = 16;
                 float ms2 = time_it([&] { probe<<<sms * cps, 128, smem>>>(in, out, sink, rows, V, mode, R, op, nst, slot); });
                 printf("  tma-ring %s cps=%d nst=%d mode=%d: %.1f us  %.0f GB/s\n", opname[op], cps, nst, mode, ms2 * 1e3, (op == 1 ? 2 : 1) * n * 4 / ms2 / 1e6);
             }

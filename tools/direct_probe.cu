@@ -1,0 +1,96 @@
+// Micro-probe: a k1-like fused sweep (row max, sum of 2^(x-max), write 2^(x-max)*scale) that reads rows with plain
+// LDG.128 straight into registers (next row prefetched into a second register set) instead of a TMA ring in shared
+// memory.  Question: does it get closer to the plain-copy bandwidth than the ring does?
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <stdint.h>
+constexpr int NT = 128, MAXC = 9;
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float4 ldg_stream(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream(float4 *p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+template <int PRE>
+__global__ void __launch_bounds__(NT) direct_k1(const float *__restrict__ in, float *__restrict__ out, int rows, int V, int mode) {
+    __shared__ float red[2][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = gridDim.x, bid = blockIdx.x;
+    const int nch = V / 4;
+    int base = rows / G, rem = rows - base * G, first = bid * base + (bid < rem ? bid : rem);
+    const int n = mode == 0 ? base + (bid < rem) : (rows - bid + G - 1) / G;
+    auto row_of = [&](int i) { return mode == 0 ? first + i : bid + i * G; };
+    float4 v[MAXC], vn[MAXC];
+    auto load = [&](float4 (&d)[MAXC], int r) {
+        const float4 *g = (const float4 *)(in + (size_t)r * V);
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) {
+            const int c = tid + k * NT;
+            d[k] = make_float4(-1e30f, -1e30f, -1e30f, -1e30f);
+            if (c < nch) d[k] = ldg_stream(g + c);
+        }
+    };
+    if (n > 0) load(v, row_of(0));
+    for (int i = 0; i < n; ++i) {
+        if (PRE && i + 1 < n) load(vn, row_of(i + 1));
+        float mx = -1e30f;
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) mx = fmaxf(mx, fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) red[i & 1][warp] = mx;
+        __syncthreads();
+        const float m = fmaxf(fmaxf(red[i & 1][0], red[i & 1][1]), fmaxf(red[i & 1][2], red[i & 1][3])) * 1.4426950f;
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) {
+            v[k].x = ex2f(fmaf(v[k].x, 1.4426950f, -m)); v[k].y = ex2f(fmaf(v[k].y, 1.4426950f, -m));
+            v[k].z = ex2f(fmaf(v[k].z, 1.4426950f, -m)); v[k].w = ex2f(fmaf(v[k].w, 1.4426950f, -m));
+            sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) red[i & 1][4 + warp] = sum;
+        __syncthreads();
+        const float sc = __frcp_rn((red[i & 1][4] + red[i & 1][5]) + (red[i & 1][6] + red[i & 1][7]));
+        float4 *o4 = (float4 *)(out + (size_t)row_of(i) * V);
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) {
+            const int c = tid + k * NT;
+            if (c < nch) stg_stream(o4 + c, make_float4(v[k].x * sc, v[k].y * sc, v[k].z * sc, v[k].w * sc));
+        }
+        if (PRE) {
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k) v[k] = vn[k];
+        } else if (i + 1 < n) load(v, row_of(i + 1));
+    }
+}
+__global__ void fill_random(float *p, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += st) { unsigned h = (unsigned)(i * 2654435761u) ^ (unsigned)(i >> 13); h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; p[i] = (float)(h & 0xffff) / 16384.f - 2.f; }
+}
+int main(int argc, char **argv) {
+    const bool rnd = argc > 1;
+    const int rows = 102400, V = 4236;
+    const size_t n = (size_t)rows * V;
+    float *in, *out;
+    cudaMalloc(&in, n * 4); cudaMalloc(&out, n * 4);
+    cudaMemset(in, 0, n * 4); cudaMemset(out, 0, n * 4);
+    if (rnd) { fill_random<<<1184, 512>>>(in, n); printf("random input data\n"); }
+    int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    auto time_it = [&](auto launch) { for (int i = 0; i < 3; ++i) launch(); cudaEventRecord(e0); for (int i = 0; i < 10; ++i) launch(); cudaEventRecord(e1); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); return ms / 10; };
+    for (int pre = 0; pre < 2; ++pre)
+        for (int mode = 0; mode < 2; ++mode)
+            for (int cps : {4, 5}) {
+                float ms = time_it([&] {
+                    if (pre) direct_k1<1><<<sms * cps, NT>>>(in, out, rows, V, mode);
+                    else direct_k1<0><<<sms * cps, NT>>>(in, out, rows, V, mode);
+                });
+                printf("direct k1-like copy prefetch=%d mode=%d cps=%d: %.1f us  %.0f GB/s\n", pre, mode, cps, ms * 1e3, 2.0 * n * 4 / ms / 1e6);
+            }
+    printf("status: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
+    return 0;
+}
