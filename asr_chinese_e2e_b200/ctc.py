@@ -134,13 +134,16 @@ def _decode_chunks(L, decode, tg, stride, chunks, T, V, umax, blank, stream, dev
 
 def _two_sweep_pipeline(ctx, L, x, tg, stride, il, tl, B, T, V, umax, blank, zi, red, inv_b, nll, grad, reduction,
                         decode=None, lattice_event=None):
-    """Default training path.  Two utterance chunks (80 % / 20 %):
+    """Default training path: ONE call (prep, fused sweep, lattice, sparse patch back to back on the caller's
+    stream; with ``lattice_event`` split after the lattice so that the caller's collective can start there).
+
+    ``CTCB200_SPLIT=s`` (0 < s < 1, experiment) cuts the batch into two utterance chunks (s / 1-s):
 
         main stream:  sweep(a)  sweep(b)            patch(a)   patch(b)
         side stream:            lattice(a)  ......  lattice(b)
 
-    lattice(a) runs under sweep(b) and lattice(b) under patch(a), so the latency-bound lattice never
-    leaves the HBM idle, and the sparse patches run after all sweeps instead of fighting them for DRAM."""
+    so that the lattice of one chunk runs under the sweep of the other.  Measured on B200 this LOSES (the lattice
+    doubles its time when it shares the memory system with a sweep), hence the default 1.0."""
     dev = x.device
     m = 4 // math.gcd(T * V, 4)                      # chunk starts must stay 16-byte aligned
     split = float(os.environ.get("CTCB200_SPLIT", "1.0"))   # measured on B200: one chunk wins (profiles/), see DESIGN.md 5

@@ -91,6 +91,15 @@ int main(int argc, char **argv) {
                 });
                 printf("direct k1-like copy prefetch=%d mode=%d cps=%d: %.1f us  %.0f GB/s\n", pre, mode, cps, ms * 1e3, 2.0 * n * 4 / ms / 1e6);
             }
+    // the same kernel with (unused) dynamic shared memory and a shared-memory carveout preference: does the size of
+    // the L1 data array left over matter for direct loads?
+    cudaFuncSetAttribute(direct_k1<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    for (int carve : {-1, 0, 25, 50, 100})
+        for (int dsm : {0, 18 * 1024, 50 * 1024}) {
+            cudaFuncSetAttribute(direct_k1<0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            float ms = time_it([&] { direct_k1<0><<<sms * 4, NT, dsm>>>(in, out, rows, V, 0); });
+            printf("direct k1-like copy cps=4 carveout=%d dyn smem=%d KB: %.1f us  %.0f GB/s\n", carve, dsm / 1024, ms * 1e3, 2.0 * n * 4 / ms / 1e6);
+        }
     printf("status: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }
