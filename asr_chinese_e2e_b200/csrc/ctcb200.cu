@@ -113,12 +113,16 @@ struct K3Args {
     float *grad; int B, T, V, Lp, blank, zero_inf;
 };
 
-template <int NT, int MAXC, bool EXACT, bool FUSED>
+template <int NT, int MAXC, bool EXACT, bool FUSED, bool DIRECT = false>
 cudaError_t launch_k1x(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
-    cudaError_t e = cudaFuncSetAttribute(k1_lse_gather<NT, MAXC, EXACT, FUSED>,
+    cudaError_t e = cudaFuncSetAttribute(k1_lse_gather<NT, MAXC, EXACT, FUSED, DIRECT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
     if (e != cudaSuccess) return e;
-    return launch_pdl(0, k1_lse_gather<NT, MAXC, EXACT, FUSED>, dim3(c.grid), dim3(NT), c.smem, s, a.logits, a.targets,
+    if (DIRECT) {   // direct loads are staged through the L1 data array even with no_allocate: leave it room
+        const int pct = env_int("CTCB200_K1F_CARVEOUT", 40);
+        cudaFuncSetAttribute(k1_lse_gather<NT, MAXC, EXACT, FUSED, DIRECT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
+    return launch_pdl(0, k1_lse_gather<NT, MAXC, EXACT, FUSED, DIRECT>, dim3(c.grid), dim3(NT), c.smem, s, a.logits, a.targets,
                       a.tnumel, a.Tb, a.Ub, a.toff, a.rowstart, a.lp_lab, a.hdr, a.B, a.T, a.V, a.Lp, a.blank, c.nst,
                       c.slot_bytes, a.grad, a.reduction, a.inv_batch, a.best, a.zero_pad_here, a.slow, a.lin_thr);
 }
@@ -129,6 +133,10 @@ cudaError_t launch_k1(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
 template <int NT, int MAXC, bool EXACT>
 cudaError_t launch_k1f(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
     return launch_k1x<NT, MAXC, EXACT, true>(c, s, a);
+}
+template <int NT, int MAXC, bool EXACT>
+cudaError_t launch_k1fd(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
+    return launch_k1x<NT, MAXC, EXACT, true, true>(c, s, a);
 }
 template <int NT, int MAXC, bool EXACT>
 cudaError_t launch_k3(const StreamCfg &c, cudaStream_t s, const K3Args &a) {
@@ -247,7 +255,13 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
         const K1Args a = {logits, targets, tnumel, Tb, Ub, toff, rowstart, lp_lab, hdr, B, T, V, g.Lp, blank,
                           fused ? fg->grad : nullptr, fused ? fg->reduction : 0, fused ? fg->inv_batch : 0.f,
                           want_argmax ? (int *)(ws + w.best) : nullptr, zero_in_lattice ? 0 : 1, slow, lin_thr};
-        if (fused) {
+        if (fused && nt1 == 128 && env_int("CTCB200_K1F_DIRECT", 0)) {
+            // direct-load sweep (experiment): no ring -> shared memory = reduction scratch, class table, one row
+            c.nst = 0; c.slot_bytes = 0;
+            c.smem = (96 + (size_t)g.Lp * 4 + 15) / 16 * 16 + align_up((size_t)V * 4 + 32, 16);
+            c.grid = dev.sms * env_int("CTCB200_K1F_CPS", 4);
+            e = STREAM_DISPATCH(launch_k1fd, 128, rounds1, exact1, c, s, a);
+        } else if (fused) {
             if (nt1 == 64) e = STREAM_DISPATCH(launch_k1f, 64, rounds1, exact1, c, s, a);
             else e = STREAM_DISPATCH(launch_k1f, 128, rounds1, exact1, c, s, a);
         } else {

@@ -66,6 +66,12 @@ __device__ __forceinline__ void tma_load_1d_hint(uint32_t dst, const void *src, 
         "l"(src), "r"(bytes), "r"(bar), "l"(policy)
         : "memory");
 }
+// streaming 16-byte load: no L1 allocation (every byte of the [B,T,V] tensors is touched once per kernel)
+__device__ __forceinline__ float4 ldg_v4_stream(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void stg_v4_hint(float4 *p, float4 v, uint64_t policy) {
     asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                  "f"(v.w), "l"(policy)

@@ -196,8 +196,13 @@ __device__ __forceinline__ void zero_padded_frames(float *__restrict__ grad, con
 // registers that hold the row (2^(x-max) is already there for the sum: one extra FMUL per element),
 // and zeroes the padded frames.  The sparse "- g_b * occupancy" part is added by k3p_patch after the
 // lattice.  This makes loss+grad TWO sweeps of [B,T,V] (read once, write once) instead of three.
-template <int NT, int MAXC, bool EXACT, bool FUSED>
-__global__ void __launch_bounds__(NT)
+// byte offset of DIRECT mode's one-row buffer in dynamic shared memory: after [red 96 B][cls_s Lp ints], 16-byte aligned
+#define DIRECT_ROWBUF_OFF(Lp) ((96 + (Lp) * 4 + 15) / 16 * 16)
+// DIRECT (experiment, off by default): the row is read with plain LDG.128 straight into the registers that hold it
+// anyway -- no shared-memory ring, no bulk copies, no mbarriers; memory-level parallelism comes from 4-5 resident
+// CTAs per SM (tools/direct_probe.cu).
+template <int NT, int MAXC, bool EXACT, bool FUSED, bool DIRECT>
+__global__ void __launch_bounds__(NT, DIRECT ? 4 : 1)
 k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targets, int64_t tnumel,
               const int *__restrict__ Tb_arr, const int *__restrict__ Ub_arr,
               const int64_t *__restrict__ toff_arr, const int *__restrict__ rowstart,
@@ -217,18 +222,20 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
     float *red = (float *)(bars + nst);              // [2 parity][3 max/sum/argmax][4 warps]
     int *cls_s = (int *)(red + 24);                  // [Lp] class id per frame slot
     const uint32_t slot0 = smem_u32(smem), bar0 = smem_u32(bars);
-    if (tid == 0) {
-        for (int s = 0; s < nst; ++s) mbar_init(bar0 + 8 * s, 1);
-        fence_mbar_init();
+    if (!DIRECT) {
+        if (tid == 0) {
+            for (int s = 0; s < nst; ++s) mbar_init(bar0 + 8 * s, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     const uintptr_t end16 = ((uintptr_t)logits + (size_t)B * T * V * 4) & ~(uintptr_t)15;
     RowCursor pc, cc;
     cursor_seek(cc, r0, rowstart, Tb_arr, B);
     pc = cc;
     int issued = 0;
-    if (tid == 0) {
+    if (!DIRECT && tid == 0) {
         for (; issued < nst && issued < nrows; ++issued) {
             issue_row(logits + ((size_t)pc.b * T + pc.t) * V, V, end16, slot0 + issued * slot_bytes,
                       bar0 + 8 * issued, 0);
@@ -263,13 +270,15 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
             }
             __syncthreads();
         }
-        mbar_wait(bar0 + 8 * stage, parity);
+        if (!DIRECT) mbar_wait(bar0 + 8 * stage, parity);
         const float *grow = logits + ((size_t)cc.b * T + cc.t) * V;
         const int head = (int)(((uintptr_t)grow & 15) >> 2);
         const int nch = (head + V + 3) >> 2;
         const unsigned char *slot = smem + (size_t)stage * slot_bytes;
-        const float4 *s4 = (const float4 *)slot;
-        const float *srow = (const float *)slot + head;
+        // the row's 16-byte hull: in the ring slot, or (DIRECT) in global memory itself
+        const float4 *s4 = DIRECT ? (const float4 *)((uintptr_t)grow & ~(uintptr_t)15) : (const float4 *)slot;
+        const float *srow = DIRECT ? grow : (const float *)slot + head;
+        auto ldrow = [&](int c) -> float4 { return DIRECT ? ldg_v4_stream(s4 + c) : s4[c]; };
 
         // interior 16-byte chunks 1..nch-2 lie wholly inside the row: no masking, one compare each;
         // the two edge chunks (shared with the neighbouring rows) are taken by threads 0 and 1
@@ -280,23 +289,30 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
             const int c = 1 + tid + k * NT;
             float4 x;
             if (EXACT && k < MAXC - 1) {
-                x = s4[c];
+                x = ldrow(c);
             } else {
                 x = make_float4(CTC_NEG_INF, CTC_NEG_INF, CTC_NEG_INF, CTC_NEG_INF);
-                if (c <= nch - 2) x = s4[c];
+                if (c <= nch - 2) x = ldrow(c);
             }
-            mx = fmaxf(mx, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
+            if (!DIRECT) mx = fmaxf(mx, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
             v[k] = x;
         }
         float4 ve = make_float4(CTC_NEG_INF, CTC_NEG_INF, CTC_NEG_INF, CTC_NEG_INF);
         if (tid == 0 || (tid == 1 && nch > 1)) {
             const int c = tid == 0 ? 0 : nch - 1;
-            ve = s4[c];
             const int e = 4 * c - head;
-            if (e < 0 || e >= V) ve.x = CTC_NEG_INF;
-            if (e + 1 < 0 || e + 1 >= V) ve.y = CTC_NEG_INF;
-            if (e + 2 < 0 || e + 2 >= V) ve.z = CTC_NEG_INF;
-            if (e + 3 < 0 || e + 3 >= V) ve.w = CTC_NEG_INF;
+            if (DIRECT) {                                  // scalar loads of the in-row elements only: the hull of the
+                if (e >= 0 && e < V) ve.x = grow[e];       // tensor's last row may end past the allocation
+                if (e + 1 >= 0 && e + 1 < V) ve.y = grow[e + 1];
+                if (e + 2 >= 0 && e + 2 < V) ve.z = grow[e + 2];
+                if (e + 3 >= 0 && e + 3 < V) ve.w = grow[e + 3];
+            } else {
+                ve = s4[c];
+                if (e < 0 || e >= V) ve.x = CTC_NEG_INF;
+                if (e + 1 < 0 || e + 1 >= V) ve.y = CTC_NEG_INF;
+                if (e + 2 < 0 || e + 2 >= V) ve.z = CTC_NEG_INF;
+                if (e + 3 < 0 || e + 3 >= V) ve.w = CTC_NEG_INF;
+            }
             mx = fmaxf(mx, fmaxf(fmaxf(ve.x, ve.y), fmaxf(ve.z, ve.w)));
         }
         // gather the frame's label logits while the row is still in the slot
@@ -307,13 +323,31 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
         for (int kk = 0; kk < MAXG; ++kk) {
             const int k = tid + kk * NT;
             cg[kk] = -1; xg[kk] = 0.f;
-            if (k < Lp) { cg[kk] = cls_s[k]; if (cg[kk] >= 0) xg[kk] = srow[cg[kk]]; }
+            if (k < Lp) { cg[kk] = cls_s[k]; if (!DIRECT && cg[kk] >= 0) xg[kk] = srow[cg[kk]]; }
+        }
+        if (DIRECT) {                                      // every load of the row is in flight before the first use
+            // the row also goes to a one-row shared-memory buffer so that the label logits can be picked from it
+            // (gathering them from global memory would re-request ~70 sectors per row: measured +70 us)
+            float4 *rb4 = (float4 *)(smem + DIRECT_ROWBUF_OFF(Lp));
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k) {
+                const int c = 1 + tid + k * NT;
+                mx = fmaxf(mx, fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w)));
+                if ((EXACT && k < MAXC - 1) || c <= nch - 2) rb4[c] = v[k];
+            }
+            if (tid == 0 || (tid == 1 && nch > 1)) rb4[tid == 0 ? 0 : nch - 1] = ve;
         }
         float *rd = red + (i & 1) * 12;
         mx = warp_max(mx);
         if (lane == 0) rd[warp] = mx;
         __syncthreads();                                   // B1: slot fully consumed
-        if (tid == 0 && issued < nrows) {                  // refill it with row i + nst
+        if (DIRECT) {
+            const float *rb = (const float *)(smem + DIRECT_ROWBUF_OFF(Lp)) + head;
+#pragma unroll
+            for (int kk = 0; kk < MAXG; ++kk)
+                if (cg[kk] >= 0) xg[kk] = rb[cg[kk]];
+        }
+        if (!DIRECT && tid == 0 && issued < nrows) {       // refill it with row i + nst
             issue_row(logits + ((size_t)pc.b * T + pc.t) * V, V, end16, slot0 + stage * slot_bytes,
                       bar0 + 8 * stage, 0);
             cursor_next(pc, Tb_arr, B);
