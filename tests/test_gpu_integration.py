@@ -250,3 +250,34 @@ def test_lattice_event_splits_the_call_without_changing_results():
         ev = torch.cuda.Event()
         ctc_loss_b200(c["logits"].cuda(), *args, reduction="mean", zero_infinity=True, lattice_event=ev)
         ev.synchronize()
+
+
+def test_forward_backward_is_cuda_graph_capturable():
+    """No host synchronisation, host-side branching on device data or allocation outside torch's allocator on
+    the default path: loss + gradient can be captured once in a CUDA graph and replayed on new data."""
+    from asr_chinese_e2e_b200 import ctc_loss_b200
+    c = make_case(24, 80, 211, 12, 77)
+    tg, il, tl = (c[k].cuda() for k in ("targets", "input_lengths", "target_lengths"))
+    x = c["logits"].cuda().requires_grad_(True)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                               # warm-up outside capture (library load, attributes)
+        for _ in range(2):
+            x.grad = None
+            ctc_loss_b200(x, tg, il, tl, reduction="mean", zero_infinity=True).backward()
+    torch.cuda.current_stream().wait_stream(side)
+    x.grad = None
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        loss = ctc_loss_b200(x, tg, il, tl, reduction="mean", zero_infinity=True)
+        loss.backward()
+    for seed in (78, 79):
+        c2 = make_case(24, 80, 211, 12, seed)
+        with torch.no_grad():
+            x.copy_(c2["logits"]); tg.copy_(c2["targets"]); il.copy_(c2["input_lengths"]); tl.copy_(c2["target_lengths"])
+        g.replay()
+        torch.cuda.synchronize()
+        rl, rg = ref_ctc(c2["logits"], c2["targets"], c2["input_lengths"], c2["target_lengths"], reduction="mean",
+                         zero_infinity=True)
+        assert abs(loss.item() - rl.item()) <= 1e-5 * abs(rl.item())
+        assert (x.grad.cpu() - rg).abs().max().item() <= 1e-4
