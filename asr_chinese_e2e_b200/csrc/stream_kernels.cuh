@@ -604,12 +604,14 @@ k3_grad(const float *__restrict__ logits, const int64_t *__restrict__ targets, i
 // exactly once -> deterministic).  Frames of utterances without a valid alignment are overwritten with
 // zeros (zero_infinity) or NaN (torch's result).  Touches ~(U+1) 32-byte sectors per 17 KB frame.
 // ------------------------------------------------------------------------------------------------
+// occ_skip: occupancies at or below it are not applied (0: only exact zeros, the states the lattice cannot reach).
+// Each skipped one saves a 32-byte DRAM read-modify-write and changes a gradient element by < occ_skip * g_b.
 template <int NT>
 __global__ void __launch_bounds__(NT)
 k3p_patch(const int64_t *__restrict__ targets, int64_t tnumel, const int *__restrict__ Tb_arr,
           const int *__restrict__ Ub_arr, const int64_t *__restrict__ toff_arr, const int *__restrict__ flags,
           const int *__restrict__ rowstart, const float *__restrict__ gam, float *__restrict__ grad,
-          int reduction, float inv_batch, int B, int T, int V, int Lp, int blank, int zero_inf) {
+          int reduction, float inv_batch, int B, int T, int V, int Lp, int blank, int zero_inf, float occ_skip) {
     extern __shared__ __align__(128) unsigned char smem[];
     int *pcls = (int *)smem;                  // [Lp] class of patch slot k (0 = blank, k>=1: label k-1)
     int *pnext = pcls + Lp;                   // [Lp] next slot with the same class, or -1
@@ -686,7 +688,7 @@ k3p_patch(const int64_t *__restrict__ targets, int64_t tnumel, const int *__rest
                     }
 #pragma unroll
                     for (int u = 0; u < 16; ++u)
-                        if (o[u] != 0.f) {
+                        if (o[u] > occ_skip) {
 #ifdef CTCB200_EXPERIMENT_PLAIN_STORE
                             gp[(size_t)(r + u) * V] = ng * o[u];          // timing experiment only (wrong values)
 #else

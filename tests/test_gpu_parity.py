@@ -378,3 +378,17 @@ def test_out_of_range_and_infeasible_utterances_fall_back_to_log_space():
     # the flags are per call: the same workspace shape on ordinary inputs is all-linear again
     _, _, stats2 = _raw_loss_grad(make_case(6, 60, 47, 9, 31338, dist="D1"))
     assert stats2 == [0, 0]
+
+
+@pytest.mark.gpu
+def test_skipping_negligible_occupancies_changes_nothing_measurable(monkeypatch):
+    """The patch kernel does not apply occupancies <= 2^-40 (each would cost a DRAM read-modify-write): against
+    applying everything but exact zeros the gradient moves by less than 2^-39 of the gradient scale."""
+    c = make_case(6, 200, 4234, 30, 606, dist="D1")
+    outs = []
+    for bits in ("0", "40"):
+        monkeypatch.setenv("CTCB200_OCC_SKIP_BITS", bits)
+        _, g = run_gpu(c, "sum")
+        outs.append(g)
+    diff = (outs[0] - outs[1]).abs().max().item()
+    assert diff <= 2.0 ** -39                                   # occupancy + at most half an ulp of the result
