@@ -30,7 +30,9 @@
  *     nll=+inf (0 with zero_infinity) exactly like torch.  Invalid lengths / labels
  *     are clamped for memory safety and reported in a device status word
  *     (ctcb200_read_status, debug use: it synchronises the stream);
- *   - deterministic: no floating-point atomics; repeated calls are bit-identical.
+ *   - deterministic: the only floating-point atomics are the sparse occupancy corrections of the fused
+ *     gradient, one per (frame, class) at most, so repeated calls are bit-identical.  Occupancies below
+ *     2^-40 (env CTCB200_OCC_SKIP_BITS) are not applied: < 1e-12 of the utterance's gradient scale.
  *
  * Limits: V >= 2, 1 <= T, 0 <= Umax <= 255, V*4 bytes must fit a shared-memory
  * stage (V <= 16384); logits / grad_logits base addresses 16-byte aligned.
