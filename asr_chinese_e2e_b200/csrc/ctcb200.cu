@@ -23,7 +23,8 @@ int env_int(const char *name, int dflt) {
     const char *s = getenv(name);
     return (s && *s) ? atoi(s) : dflt;
 }
-// bit 0: sweep after prep (measured: +70 us per step in a back-to-back loop), bit 1: lattice after sweep,
+// bit 0: sweep after prep (measured: +70 us per step in a back-to-back loop; also not safe as is: the sweep reads
+// k0_prep's arrays through const __restrict__ pointers, i.e. possibly non-coherent loads), bit 1: lattice after sweep,
 // bit 2: patch after lattice (its class tables are built while the lattice drains: -5 us)
 const int g_use_pdl = env_int("CTCB200_PDL", 6);
 
