@@ -481,10 +481,10 @@ k2_lattice(const int64_t *__restrict__ targets, int64_t tnumel, const int *__res
     const int pair = warp >> 1, dir = warp & 1;
     const int b = 2 * blockIdx.x + pair;
     if (b >= B) return;                                          // odd batch: the last CTA has one utterance
-    const int Tb = Tb_arr[b], Ub = Ub_arr[b];
+    const int Tb = __ldcg(Tb_arr + b), Ub = __ldcg(Ub_arr + b);   // (ld.global.cg: see stream_kernels.cuh, cursor helpers)
 
     if (Tb > 0) {
-        const int64_t toff = toff_arr[b];
+        const int64_t toff = __ldcg(toff_arr + b);
         // fast path: linear-domain recursion; utterances outside its range (slow[b], set by the sweep) or whose
         // likelihood underflows (which includes the infeasible ones) run the log-space recursion
         unsigned char *ab_utt = (unsigned char *)ab_ws + (size_t)b * ab_utt_bytes;
@@ -530,7 +530,7 @@ k2_lattice(const int64_t *__restrict__ targets, int64_t tnumel, const int *__res
             float s_norm = 0.f, s_sum = 0.f;
             for (int i = lane; i < B; i += 32) {
                 const float v = __ldcg(nll + i);
-                const int u = Ub_arr[i];
+                const int u = __ldcg(Ub_arr + i);
                 s_sum += v;
                 s_norm += v / (float)(u > 1 ? u : 1);
             }

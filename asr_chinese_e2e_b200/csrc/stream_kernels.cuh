@@ -84,22 +84,29 @@ __global__ void __launch_bounds__(1024) k0_prep(const int64_t *__restrict__ in_l
 
 // ------------------------------------------------------------------------------------------------
 // valid-frame cursor: flattened index over frames t < Tb[b]  <->  (b, t)
+// (k0_prep's arrays are read with ld.global.cg everywhere: kernels launched with programmatic stream serialization
+//  must not rely on the SM's L1 / non-coherent cache having been invalidated since those arrays were written)
 // ------------------------------------------------------------------------------------------------
 struct RowCursor {
     int b, t, Tb;
 };
+// COHERENT: ld.global.cg (see above) -- used by the kernels that may start before their predecessor has drained
+template <bool COHERENT = false>
+__device__ __forceinline__ int ld_prep(const int *p) { return COHERENT ? __ldcg(p) : *p; }
+template <bool COHERENT = false>
 __device__ __forceinline__ void cursor_seek(RowCursor &c, int row, const int *__restrict__ rowstart,
                                             const int *__restrict__ Tb_arr, int B) {
     int lo = 0, hi = B - 1;   // smallest b with rowstart[b+1] > row
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (rowstart[mid + 1] > row) hi = mid; else lo = mid + 1;
+        if (ld_prep<COHERENT>(rowstart + mid + 1) > row) hi = mid; else lo = mid + 1;
     }
-    c.b = lo; c.t = row - rowstart[lo]; c.Tb = Tb_arr[lo];
+    c.b = lo; c.t = row - ld_prep<COHERENT>(rowstart + lo); c.Tb = ld_prep<COHERENT>(Tb_arr + lo);
 }
+template <bool COHERENT = false>
 __device__ __forceinline__ void cursor_next(RowCursor &c, const int *__restrict__ Tb_arr, int B) {
     c.t++;
-    while (c.t >= c.Tb && c.b + 1 < B) { c.b++; c.t = 0; c.Tb = Tb_arr[c.b]; }
+    while (c.t >= c.Tb && c.b + 1 < B) { c.b++; c.t = 0; c.Tb = ld_prep<COHERENT>(Tb_arr + c.b); }
 }
 
 // Balanced split of n items over the grid with 32-bit arithmetic only (a 64-bit division would be a
@@ -621,19 +628,19 @@ k3p_patch(const int64_t *__restrict__ targets, int64_t tnumel, const int *__rest
     // before the lattice kernel itself could start), so the class tables of the first segment are built early.
     bool waited = false;
     int r0, nrows;
-    grid_share(rowstart[B], r0, nrows);
+    grid_share(__ldcg(rowstart + B), r0, nrows);
     if (nrows <= 0) return;
     RowCursor cc;
-    cursor_seek(cc, r0, rowstart, Tb_arr, B);
+    cursor_seek<true>(cc, r0, rowstart, Tb_arr, B);
     constexpr int MAXP = 256 / NT;
     int i = 0;
     while (i < nrows) {                        // one utterance segment of this CTA's frame range per iteration
         const int b = cc.b, t0 = cc.t;
         const int seg = (cc.Tb - t0) < (nrows - i) ? (cc.Tb - t0) : (nrows - i);
-        const int Ub = Ub_arr[b];
+        const int Ub = __ldcg(Ub_arr + b);
         float *gbase = grad + ((size_t)b * T + t0) * V;
         const float g = reduction == 1 ? inv_batch * __frcp_rn((float)(Ub > 1 ? Ub : 1)) : 1.f;
-        const int64_t toff = toff_arr[b];
+        const int64_t toff = __ldcg(toff_arr + b);
         __syncthreads();                       // previous segment's table reads are done
         for (int k = tid; k <= Ub; k += NT) {
             long long c = blank;
@@ -700,7 +707,7 @@ k3p_patch(const int64_t *__restrict__ targets, int64_t tnumel, const int *__rest
         }
         i += seg;
         cc.t += seg - 1;
-        cursor_next(cc, Tb_arr, B);
+        cursor_next<true>(cc, Tb_arr, B);
     }
 }
 
