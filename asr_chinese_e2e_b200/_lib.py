@@ -51,6 +51,8 @@ _FWD_ARGS = [_p, _p, _i64, _i64, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz
 SIGNATURES = {
     "ctcb200_version": (_i, []),
     "ctcb200_strerror": (ctypes.c_char_p, [_i]),
+    "ctcb200_set_option": (_i, [ctypes.c_char_p, _i]),
+    "ctcb200_get_option": (_i, [ctypes.c_char_p, ctypes.POINTER(_i)]),
     "ctcb200_workspace_bytes": (_i, [_i, _i, _i, _i, ctypes.POINTER(_sz)]),
     "ctcb200_forward": (_i, _FWD_ARGS),
     "ctcb200_loss_only": (_i, _FWD_ARGS),
@@ -59,6 +61,7 @@ SIGNATURES = {
     "ctcb200_backward": (_i, [_p, _p, _i64, _i64, _p, _i64, _i, _f, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "ctcb200_rescale_grad": (_i, [_p, _p, _i64, _p, _p, _i, _i, _i, _p]),
     "ctcb200_greedy_decode": (_i, [_p, _i64, _i64, _i, _i, _i, _i, _i, _p, _sz, _p, _p, _p, _p]),
+    "ctcb200_edit_distance": (_i, [_p, _i64, _p, _i64, _i, _i, _i, _i, _p, _p, _p]),
     "ctcb200_ce_workspace_bytes": (_i, [_i64, ctypes.POINTER(_sz)]),
     "ctcb200_ce_loss_grad": (_i, [_p, _p, _i64, _i, _i, _f, _f, _p, _p, _p, _sz, _p]),
     "ctcb200_read_status": (_i, [_p, ctypes.POINTER(_i), _p]),
@@ -91,6 +94,18 @@ def strerror(code: int) -> str:
 def check(code: int, what: str) -> None:
     if code != 0:
         raise CtcB200Error(f"{what} failed: [{code}] {strerror(code)}")
+
+
+def set_option(name: str, value: int) -> None:
+    """Developer tunable of the library; the CTCB200_* environment variables are read once,
+    when the library is loaded -- afterwards this is the way to change one."""
+    check(lib().ctcb200_set_option(name.encode(), int(value)), f"ctcb200_set_option({name})")
+
+
+def get_option(name: str) -> int:
+    out = _i(0)
+    check(lib().ctcb200_get_option(name.encode(), ctypes.byref(out)), f"ctcb200_get_option({name})")
+    return int(out.value)
 
 
 def workspace_bytes(B: int, T: int, V: int, Umax: int) -> int:

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "ce_kernel.cuh"
 #include "decode_kernel.cuh"
@@ -19,14 +20,42 @@ namespace {
 constexpr int kMaxV = 16384;
 constexpr size_t kSmemBudget = 226 * 1024;   // leave 1 KB of the 227 KB opt-in limit to the driver
 
-int env_int(const char *name, int dflt) {
-    const char *s = getenv(name);
-    return (s && *s) ? atoi(s) : dflt;
-}
-// bit 0: sweep after prep (measured: +70 us per step in a back-to-back loop; also not safe as is: the sweep reads
-// k0_prep's arrays through const __restrict__ pointers, i.e. possibly non-coherent loads), bit 1: lattice after sweep,
-// bit 2: patch after lattice (its class tables are built while the lattice drains: -5 us)
-const int g_use_pdl = env_int("CTCB200_PDL", 6);
+// Developer tunables.  Every knob is read from the environment ONCE, when the library is loaded; afterwards
+// ctcb200_set_option / ctcb200_get_option (include/ctcb200.h) are the only way to change one.  0 = "auto" for the
+// launch-shape knobs (the tuned default of the kernel in question).
+enum OptId {
+    OPT_PDL, OPT_LATTICE_LOG, OPT_LIN_THR, OPT_K1F_NT, OPT_K1F_NST, OPT_K1F_CPS, OPT_K1_NT, OPT_K1_NST, OPT_K1_CPS,
+    OPT_K3_NT, OPT_K3_NST, OPT_K3_CPS, OPT_CE_NST, OPT_CE_CPS, OPT_K3P_CPS, OPT_OCC_SKIP_BITS, OPT_K1F_DIRECT,
+    OPT_K1F_CARVEOUT, OPT_ZERO_IN_LATTICE, OPT_ZERO_CPS, OPT_SKIP_LATTICE, OPT_LABEL_KEEP_L2, OPT_COUNT
+};
+struct Opt { const char *name, *env; int value; };
+Opt g_opt[OPT_COUNT] = {
+    // bit 0: sweep after prep (measured: +70 us per step in a back-to-back loop; also not safe as is: the sweep reads
+    // k0_prep's arrays through const __restrict__ pointers, i.e. possibly non-coherent loads), bit 1: lattice after
+    // sweep, bit 2: patch after lattice (its class tables are built while the lattice drains: -5 us)
+    {"pdl", "CTCB200_PDL", 6},
+    {"lattice_log", "CTCB200_LATTICE_LOG", 0},          // 1: log-space recursion for every utterance
+    {"lin_thr", "CTCB200_LIN_THR", 0},                  // range limit of the linear-domain lattice (bits; 0 = auto)
+    {"k1f_nt", "CTCB200_K1F_NT", 0}, {"k1f_nst", "CTCB200_K1F_NST", 0}, {"k1f_cps", "CTCB200_K1F_CPS", 0},
+    {"k1_nt", "CTCB200_K1_NT", 0}, {"k1_nst", "CTCB200_K1_NST", 0}, {"k1_cps", "CTCB200_K1_CPS", 0},
+    {"k3_nt", "CTCB200_K3_NT", 0}, {"k3_nst", "CTCB200_K3_NST", 0}, {"k3_cps", "CTCB200_K3_CPS", 0},
+    {"ce_nst", "CTCB200_CE_NST", 0}, {"ce_cps", "CTCB200_CE_CPS", 0},
+    {"k3p_cps", "CTCB200_K3P_CPS", 32},
+    {"occ_skip_bits", "CTCB200_OCC_SKIP_BITS", 40},     // the patch skips occupancies <= 2^-bits (0: exact zeros only)
+    {"k1f_direct", "CTCB200_K1F_DIRECT", 0}, {"k1f_carveout", "CTCB200_K1F_CARVEOUT", 40},
+    {"zero_in_lattice", "CTCB200_ZERO_IN_LATTICE", 0}, {"zero_cps", "CTCB200_ZERO_CPS", 2},
+    {"skip_lattice", "CTCB200_DEBUG_SKIP_LATTICE", 0},  // profiling aid: time the sweep alone
+    {"label_keep_l2", "CTCB200_LABEL_KEEP_L2", 1},      // fused sweep: evict_last for gradient chunks the patch revisits
+};
+const bool g_opt_loaded = [] {
+    for (Opt &o : g_opt) {
+        const char *s = getenv(o.env);
+        if (s && *s) o.value = atoi(s);
+    }
+    return true;
+}();
+inline int opt(OptId id) { return g_opt[id].value; }
+inline int opt_or(OptId id, int dflt) { return g_opt[id].value > 0 ? g_opt[id].value : dflt; }
 
 struct DevInfo {
     int sms;
@@ -69,10 +98,10 @@ struct StreamCfg {
 // CTA of another utterance chunk can be co-resident.
 constexpr size_t kLatticeReserve = 52 * 1024;
 int stream_cfg(int V, uint32_t stage_extra, size_t fixed_extra, int sms, int dflt_nst, int dflt_cps,
-               const char *env_nst, const char *env_cps, StreamCfg *c) {
+               OptId opt_nst, OptId opt_cps, StreamCfg *c) {
     c->slot_bytes = (uint32_t)align_up((size_t)V * 4 + 32, 128);
     c->stage_bytes = c->slot_bytes + stage_extra;
-    int nst = env_int(env_nst, dflt_nst);
+    int nst = opt_or(opt_nst, dflt_nst);
     if (nst < 2) nst = 2;
     if (nst > 8) nst = 8;
     while (nst > 2 && (size_t)nst * c->stage_bytes + fixed_extra + 8 * nst > kSmemBudget) --nst;
@@ -82,7 +111,7 @@ int stream_cfg(int V, uint32_t stage_extra, size_t fixed_extra, int sms, int dfl
     int cps = (int)((kSmemBudget - kLatticeReserve) / (c->smem + 1024));   // + per-CTA reserved shared memory
     if (cps > dflt_cps) cps = dflt_cps;
     if (cps < 1) cps = 1;
-    cps = env_int(env_cps, cps);
+    cps = opt_or(opt_cps, cps);
     if (cps < 1) cps = 1;
     c->grid = sms * cps;
     return 0;
@@ -98,7 +127,7 @@ cudaError_t launch_pdl(int edge, void (*kernel)(KArgs...), dim3 grid, dim3 block
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = edge >= 0 ? (g_use_pdl >> edge) & 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = edge >= 0 ? (opt(OPT_PDL) >> edge) & 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
@@ -107,12 +136,12 @@ struct K1Args {
     const float *logits; const int64_t *targets; int64_t tnumel; const int *Tb, *Ub; const int64_t *toff;
     const int *rowstart; float *lp_lab; int *hdr; int B, T, V, Lp, blank;
     float *grad; int reduction; float inv_batch;   // fused (2-sweep) mode only
-    int *best; int zero_pad_here; int *slow; float lin_thr;
+    int *best; int zero_pad_here; int *slow; float lin_thr; int *bad;
 };
 struct K3Args {
     const float *logits; const int64_t *targets; int64_t tnumel; const int *Tb, *Ub; const int64_t *toff;
     const int *flags, *rowstart; const float *gam, *grad_out; int64_t go_stride; int reduction; float inv_batch;
-    float *grad; int B, T, V, Lp, blank, zero_inf;
+    float *grad; int B, T, V, Lp, blank, zero_inf; const int *bad;
 };
 
 template <int NT, int MAXC, bool EXACT, bool FUSED, bool DIRECT = false>
@@ -121,12 +150,12 @@ cudaError_t launch_k1x(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
     if (e != cudaSuccess) return e;
     if (DIRECT) {   // direct loads are staged through the L1 data array even with no_allocate: leave it room
-        const int pct = env_int("CTCB200_K1F_CARVEOUT", 40);
+        const int pct = opt(OPT_K1F_CARVEOUT);
         cudaFuncSetAttribute(k1_lse_gather<NT, MAXC, EXACT, FUSED, DIRECT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     }
     return launch_pdl(0, k1_lse_gather<NT, MAXC, EXACT, FUSED, DIRECT>, dim3(c.grid), dim3(NT), c.smem, s, a.logits, a.targets,
                       a.tnumel, a.Tb, a.Ub, a.toff, a.rowstart, a.lp_lab, a.hdr, a.B, a.T, a.V, a.Lp, a.blank, c.nst,
-                      c.slot_bytes, a.grad, a.reduction, a.inv_batch, a.best, a.zero_pad_here, a.slow, a.lin_thr);
+                      c.slot_bytes, a.grad, a.reduction, a.inv_batch, a.best, a.zero_pad_here, a.slow, a.lin_thr, a.bad);
 }
 template <int NT, int MAXC, bool EXACT>
 cudaError_t launch_k1(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
@@ -148,7 +177,7 @@ cudaError_t launch_k3(const StreamCfg &c, cudaStream_t s, const K3Args &a) {
     k3_grad<NT, MAXC, EXACT><<<c.grid, NT, c.smem, s>>>(a.logits, a.targets, a.tnumel, a.Tb, a.Ub, a.toff, a.flags,
                                                         a.rowstart, a.gam, a.grad_out, a.go_stride, a.reduction,
                                                         a.inv_batch, a.grad, a.B, a.T, a.V, a.Lp, a.blank, a.zero_inf,
-                                                        c.nst, c.slot_bytes, c.stage_bytes);
+                                                        c.nst, c.slot_bytes, c.stage_bytes, a.bad);
     return cudaGetLastError();
 }
 
@@ -176,13 +205,13 @@ cudaError_t launch_k2(cudaStream_t s, const int64_t *targets, int64_t tnumel, co
                       const int64_t *toff, int *flags, const float *lp_lab, float *gam, float *ab, float *nll,
                       float *loss_sums, unsigned *ticket, int B, int T, int zero_inf, float *zero_grad,
                       const int *rowstart, int V, int zero_ctas, double *tile_off, float mean_scale, const int *slow,
-                      size_t ab_utt, bool follows_sweep) {
+                      size_t ab_utt, bool follows_sweep, const int *bad) {
     constexpr uint32_t smem = k2_smem_bytes<NS, GRAD>();
     cudaError_t e = cudaFuncSetAttribute(k2_lattice<NS, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return launch_pdl(follows_sweep ? 1 : -1, k2_lattice<NS, GRAD>, dim3((B + 1) / 2 + (zero_grad ? zero_ctas : 0)), dim3(128), smem, s,
                       targets, tnumel, Tb, Ub, toff, flags, lp_lab, gam, ab, nll, loss_sums, ticket, B, T, zero_inf,
-                      zero_grad, rowstart, V, tile_off, mean_scale, slow, ab_utt);
+                      zero_grad, rowstart, V, tile_off, mean_scale, slow, ab_utt, bad);
 }
 
 struct FusedGrad {          // non-null grad => 2-sweep mode: the sweep writes g*softmax, k3p adds -g*occupancy
@@ -217,14 +246,14 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     int *Tb = (int *)(ws + w.Tb), *Ub = (int *)(ws + w.Ub), *flags = (int *)(ws + w.flags);
     int64_t *toff = (int64_t *)(ws + w.toff);
     int *rowstart = (int *)(ws + w.rowstart);
-    int *slow = (int *)(ws + w.slow);
+    int *slow = (int *)(ws + w.slow), *bad = (int *)(ws + w.bad);
     float *lp_lab = (float *)(ws + w.lp_lab), *gam = (float *)(ws + w.gam), *ab = (float *)(ws + w.ab);
     const int64_t tnumel = targets_stride ? (int64_t)B * targets_stride : targets_numel;
     // Range of the linear-domain lattice (lattice_lin.cuh): a stage of TT frames plus the NS/2 labels of one lane
     // may shrink a value by (TT + NS/2) * |lp| binary orders; keep that inside ~900 of a double's 1022.
-    // CTCB200_LATTICE_LOG=1 forces the log-space recursion for every utterance.
-    static const int lattice_mode = env_int("CTCB200_LATTICE_LOG", 0);
-    static const int thr_env = env_int("CTCB200_LIN_THR", 0);
+    // CTCB200_FLAG_LATTICE_LOG (per call) or the lattice_log option forces the log-space recursion for every utterance.
+    const int lattice_mode = opt(OPT_LATTICE_LOG) || (zero_infinity & CTCB200_FLAG_LATTICE_LOG);
+    const int thr_env = opt(OPT_LIN_THR);
     const float lin_thr = lattice_mode ? 1.f
                                        : -(float)(thr_env > 0 ? thr_env : 900 / (lin_tile_frames(g.NS) + g.NS / 2));
 
@@ -235,33 +264,33 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     // experiment (off by default): write the zeros of the padded frames from extra CTAs of the lattice launch,
     // where the HBM is otherwise idle.  Measured on B200: the sweep gets 75 us shorter and the lattice 77 us
     // longer -- any co-resident memory traffic doubles the latency-bound lattice -- so nothing is gained.
-    const bool zero_in_lattice = fused && stages == 7 && env_int("CTCB200_ZERO_IN_LATTICE", 0);
+    const bool zero_in_lattice = fused && stages == 7 && opt(OPT_ZERO_IN_LATTICE);
     cudaError_t e = cudaSuccess;
     if (stages & 1) {
     prefer_max_carveout(k0_prep);
-    k0_prep<<<1, 1024, 0, s>>>(in_len, tgt_len, targets_stride, B, T, Umax, hdr, Tb, Ub, flags, toff, rowstart, slow);
+    k0_prep<<<1, 1024, 0, s>>>(in_len, tgt_len, targets_stride, B, T, Umax, hdr, Tb, Ub, flags, toff, rowstart, slow, bad);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
 
     StreamCfg c;
     int nt1, rounds1;
     bool exact1;
-    stream_pick(V, env_int(fused ? "CTCB200_K1F_NT" : "CTCB200_K1_NT", fused ? 128 : 64), &nt1, &rounds1, &exact1);
+    stream_pick(V, fused ? opt_or(OPT_K1F_NT, 128) : opt_or(OPT_K1_NT, 64), &nt1, &rounds1, &exact1);
     if (fused)
-        rc = stream_cfg(V, 0, 96 + (size_t)g.Lp * 4, dev.sms, 4, 2, "CTCB200_K1F_NST", "CTCB200_K1F_CPS", &c);
+        rc = stream_cfg(V, 0, 96 + (size_t)g.Lp * 4, dev.sms, 4, 2, OPT_K1F_NST, OPT_K1F_CPS, &c);
     else
         rc = stream_cfg(V, 0, 96 + (size_t)g.Lp * 4, dev.sms, nt1 == 64 ? 2 : 3, nt1 == 64 ? 5 : 3,
-                        "CTCB200_K1_NST", "CTCB200_K1_CPS", &c);
+                        OPT_K1_NST, OPT_K1_CPS, &c);
     if (rc) return rc;
     {
         const K1Args a = {logits, targets, tnumel, Tb, Ub, toff, rowstart, lp_lab, hdr, B, T, V, g.Lp, blank,
                           fused ? fg->grad : nullptr, fused ? fg->reduction : 0, fused ? fg->inv_batch : 0.f,
-                          want_argmax ? (int *)(ws + w.best) : nullptr, zero_in_lattice ? 0 : 1, slow, lin_thr};
-        if (fused && nt1 == 128 && env_int("CTCB200_K1F_DIRECT", 0)) {
+                          want_argmax ? (int *)(ws + w.best) : nullptr, zero_in_lattice ? 0 : 1, slow, lin_thr, bad};
+        if (fused && nt1 == 128 && opt(OPT_K1F_DIRECT)) {
             // direct-load sweep (experiment): no ring -> shared memory = reduction scratch, class table, one row
             c.nst = 0; c.slot_bytes = 0;
             c.smem = (96 + (size_t)g.Lp * 4 + 15) / 16 * 16 + align_up((size_t)V * 4 + 32, 16);
-            c.grid = dev.sms * env_int("CTCB200_K1F_CPS", 4);
+            c.grid = dev.sms * opt_or(OPT_K1F_CPS, 4);
             e = STREAM_DISPATCH(launch_k1fd, 128, rounds1, exact1, c, s, a);
         } else if (fused) {
             if (nt1 == 64) e = STREAM_DISPATCH(launch_k1f, 64, rounds1, exact1, c, s, a);
@@ -275,12 +304,12 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     if (sweep_done && (e = cudaEventRecord((cudaEvent_t)sweep_done, s)) != cudaSuccess) return (int)e;
     }   // stage: sweep
 
-    if (env_int("CTCB200_DEBUG_SKIP_LATTICE", 0)) return CTCB200_OK;   // profiling aid: time the sweep alone
+    if (opt(OPT_SKIP_LATTICE)) return CTCB200_OK;   // profiling aid: time the sweep alone
     if (stages & 2) {
     unsigned *ticket = (unsigned *)(hdr + 1);
 #define K2_ARGS s, targets, tnumel, Tb, Ub, toff, flags, lp_lab, gam, ab, nll, loss_sums, ticket, B, T, zero_infinity, \
-                (zero_in_lattice ? fg->grad : nullptr), rowstart, V, dev.sms * env_int("CTCB200_ZERO_CPS", 2),   \
-                (double *)(ws + w.tile_off), (fused ? fg->inv_batch : 1.f / (float)B), slow, w.ab_utt, ((stages & 1) && !sweep_done)
+                (zero_in_lattice ? fg->grad : nullptr), rowstart, V, dev.sms * opt_or(OPT_ZERO_CPS, 2),   \
+                (double *)(ws + w.tile_off), (fused ? fg->inv_batch : 1.f / (float)B), slow, w.ab_utt, ((stages & 1) && !sweep_done), bad
     if (want_grad) {
         if (g.NS == 4) e = launch_k2<4, true>(K2_ARGS);
         else if (g.NS == 8) e = launch_k2<8, true>(K2_ARGS);
@@ -294,17 +323,17 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     }   // stage: lattice
     if (e != cudaSuccess || !fused || !(stages & 4)) return (int)e;
     {
-        const int per = env_int("CTCB200_K3P_CPS", 32);
+        const int per = opt_or(OPT_K3P_CPS, 32);
         // occupancies <= 2^-bits are not applied to the gradient: at the default 40 that is < 1e-12 of the utterance's
         // gradient scale (fp32 resolves 3e-11 at a softmax value of 1/V; the parity bar is 1e-4 absolute), and on
         // diffuse posteriors it is a third of all (frame, class) pairs, each a 32-byte DRAM read-modify-write.
         // CTCB200_OCC_SKIP_BITS=0 applies everything but exact zeros.
-        const int skip_bits = env_int("CTCB200_OCC_SKIP_BITS", 40);
+        const int skip_bits = opt(OPT_OCC_SKIP_BITS);
         const float occ_skip = skip_bits > 0 ? ldexpf(1.f, -skip_bits) : 0.f;
         const size_t smem = 2 * (size_t)g.Lp * 4;
         prefer_max_carveout(k3p_patch<64>);
         e = launch_pdl((stages & 2) ? 2 : -1, k3p_patch<64>, dim3(dev.sms * (per < 1 ? 1 : per)), dim3(64), smem, s, targets, tnumel, Tb, Ub, toff,
-                       flags, rowstart, gam, fg->grad, fg->reduction, fg->inv_batch, B, T, V, g.Lp, blank, zero_infinity, occ_skip);
+                       flags, rowstart, gam, fg->grad, fg->reduction, fg->inv_batch, B, T, V, g.Lp, blank, zero_infinity, occ_skip, bad);
     }
     return (int)e;
 }
@@ -346,10 +375,25 @@ const char *ctcb200_strerror(int code) {
         case CTCB200_ERR_REDUCTION: return "unknown reduction code";
         case CTCB200_ERR_WORKSPACE: return "workspace too small (see ctcb200_workspace_bytes)";
         case CTCB200_ERR_NO_DEVICE: return "no CUDA device with compute capability 10.x (sm_100a) is current";
+        case CTCB200_ERR_OPTION: return "unknown option name";
         default: break;
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
     return "unknown ctcb200 error";
+}
+
+int ctcb200_set_option(const char *name, int value) {
+    if (!name) return CTCB200_ERR_NULL;
+    for (Opt &o : g_opt)
+        if (!strcmp(o.name, name)) { o.value = value; return CTCB200_OK; }
+    return CTCB200_ERR_OPTION;
+}
+
+int ctcb200_get_option(const char *name, int *value) {
+    if (!name || !value) return CTCB200_ERR_NULL;
+    for (const Opt &o : g_opt)
+        if (!strcmp(o.name, name)) { *value = o.value; return CTCB200_OK; }
+    return CTCB200_ERR_OPTION;
 }
 
 int ctcb200_workspace_bytes(int B, int T, int V, int Umax, size_t *out_bytes) {
@@ -432,15 +476,16 @@ int ctcb200_backward(const float *logits, const int64_t *targets, int64_t target
 
     StreamCfg c;
     const uint32_t gam_stage = (uint32_t)align_up((size_t)g.Lp * 4, 128);
-    if ((rc = stream_cfg(V, gam_stage, 3 * (size_t)g.Lp * 4, dev.sms, 3, 3, "CTCB200_K3_NST", "CTCB200_K3_CPS", &c)))
+    if ((rc = stream_cfg(V, gam_stage, 3 * (size_t)g.Lp * 4, dev.sms, 3, 3, OPT_K3_NST, OPT_K3_CPS, &c)))
         return rc;
     cudaError_t e;
     {
         const K3Args a = {logits, targets, tnumel, Tb, Ub, toff, flags, rowstart, gam, grad_out, grad_out_stride,
-                          reduction, inv_batch, grad_logits, B, T, V, g.Lp, blank, zero_infinity};
+                          reduction, inv_batch, grad_logits, B, T, V, g.Lp, blank, zero_infinity,
+                          (const int *)(ws + w.bad)};
         int nt, rounds;
         bool exact;
-        stream_pick(V, env_int("CTCB200_K3_NT", 128), &nt, &rounds, &exact);
+        stream_pick(V, opt_or(OPT_K3_NT, 128), &nt, &rounds, &exact);
         if (nt == 64) e = STREAM_DISPATCH(launch_k3, 64, rounds, exact, c, s, a);
         else e = STREAM_DISPATCH(launch_k3, 128, rounds, exact, c, s, a);
     }
@@ -501,6 +546,34 @@ int ctcb200_greedy_decode(const int64_t *targets, int64_t targets_stride, int64_
     return (int)e;
 }
 
+int ctcb200_edit_distance(const int64_t *hyp, int64_t hyp_stride, const int64_t *gold, int64_t gold_stride, int B,
+                          int L, int pad, int mode, int *edit_out, int *words_out, ctcb200_stream_t stream) {
+    if (!hyp || !gold || !edit_out || !words_out) return CTCB200_ERR_NULL;
+    if (B < 0 || L < 1 || hyp_stride < L || gold_stride < L || mode < 0 || mode > 1) return CTCB200_ERR_SHAPE;
+    const int nsym = mode ? 2 * L - 1 : L;
+    if (nsym > 32 * 32) return CTCB200_ERR_UMAX;
+    if (B == 0) return CTCB200_OK;
+    const size_t smem = 4 * 2 * (size_t)L * sizeof(int);
+    const int grid = (B + 3) / 4;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e;
+#define K6(N)                                                                                                     \
+    do {                                                                                                          \
+        e = cudaFuncSetAttribute(k6_seq_edit<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+        if (e == cudaSuccess) {                                                                                   \
+            k6_seq_edit<N><<<grid, 128, smem, s>>>(hyp, hyp_stride, gold, gold_stride, B, L, pad, mode, edit_out, \
+                                                   words_out);                                                    \
+            e = cudaGetLastError();                                                                               \
+        }                                                                                                         \
+    } while (0)
+    if (nsym <= 128) K6(4);
+    else if (nsym <= 256) K6(8);
+    else if (nsym <= 512) K6(16);
+    else K6(32);
+#undef K6
+    return (int)e;
+}
+
 // ---- attention-branch cross-entropy -------------------------------------------
 static size_t ce_ws_layout(int64_t rows, size_t *o_vlist, size_t *o_plist, size_t *o_rowloss) {
     size_t o = kAlign;                      // hdr
@@ -542,7 +615,7 @@ int ctcb200_ce_loss_grad(const float *pred, const int64_t *gold, int64_t rows, i
     int nt, rounds;
     bool exact;
     stream_pick(V, 128, &nt, &rounds, &exact);
-    if ((rc = stream_cfg(V, 0, 128, dev.sms, grad ? 4 : 3, grad ? 2 : 4, "CTCB200_CE_NST", "CTCB200_CE_CPS", &c))) return rc;
+    if ((rc = stream_cfg(V, 0, 128, dev.sms, grad ? 4 : 3, grad ? 2 : 4, OPT_CE_NST, OPT_CE_CPS, &c))) return rc;
     e = STREAM_DISPATCH(launch_kce, 128, rounds, exact, c, s, grad != nullptr, pred, gold, (int)rows, V, hdr, vlist, plist,
                         rowloss, grad, smoothing, weight);
     if (e != cudaSuccess) return (int)e;

@@ -465,7 +465,8 @@ k2_lattice(const int64_t *__restrict__ targets, int64_t tnumel, const int *__res
            const float *__restrict__ lp_lab, float *__restrict__ gam, float *__restrict__ ab_ws,
            float *__restrict__ nll, float *__restrict__ loss_sums, unsigned *__restrict__ ticket, int B,
            int T, int zero_inf, float *__restrict__ zero_grad, const int *__restrict__ rowstart, int V,
-           double *__restrict__ tile_off, float mean_scale, const int *__restrict__ slow, size_t ab_utt_bytes) {
+           double *__restrict__ tile_off, float mean_scale, const int *__restrict__ slow, size_t ab_utt_bytes,
+           const int *__restrict__ bad_arr) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     griddep_wait();                                              // the sweep's lp_lab frames
@@ -519,6 +520,10 @@ k2_lattice(const int64_t *__restrict__ targets, int64_t tnumel, const int *__res
         nll[b] = (Ub == 0) ? 0.f : (zero_inf ? 0.f : __int_as_float(0x7f800000));
         flags[b] = (Ub != 0);
     }
+
+    // invalid lengths / labels (clamped for memory safety by k0_prep / the sweep): F.ctc_loss raises on such inputs;
+    // here the utterance's nll -- and with it every reduced loss -- becomes NaN, so the error cannot go unnoticed
+    if (dir == 0 && lane == 0 && __ldcg(bad_arr + b)) nll[b] = __int_as_float(0x7fc00000);
 
     // ---- deterministic batch reduction by the last utterance to finish ----
     if (loss_sums != nullptr && dir == 0) {

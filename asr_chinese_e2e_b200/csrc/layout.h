@@ -55,6 +55,8 @@ struct Workspace {
     size_t Ub;        // int[B]   clamped target lengths
     size_t flags;     // int[B]   1 = infeasible (no valid alignment)
     size_t slow;      // int[B]   1 = some gathered log-probability is outside the linear-domain lattice's range
+    size_t bad;       // int[B]   != 0: invalid input (length out of range, label out of range or == blank): the
+                      //          utterance's nll and gradient are poisoned with NaN (F.ctc_loss raises on these)
     size_t toff;      // int64[B] element offset of utterance b's labels in `targets`
     size_t rowstart;  // int[B+1] exclusive prefix sum of Tb (valid-frame numbering)
     size_t lp_lab;    // float[B*T*Lp]
@@ -75,6 +77,7 @@ static inline Workspace workspace_layout(int B, int T, const Geom &g) {
     w.Ub = o;        o += align_up(sizeof(int) * b);
     w.flags = o;     o += align_up(sizeof(int) * b);
     w.slow = o;      o += align_up(sizeof(int) * b);
+    w.bad = o;       o += align_up(sizeof(int) * b);
     w.toff = o;      o += align_up(sizeof(int64_t) * b);
     w.rowstart = o;  o += align_up(sizeof(int) * (b + 1));
     w.lp_lab = o;    o += align_up(sizeof(float) * b * T * g.Lp);

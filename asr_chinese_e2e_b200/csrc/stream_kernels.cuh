@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(1024) k0_prep(const int64_t *__restrict__ in_l
                                                 int *__restrict__ hdr, int *__restrict__ Tb_arr,
                                                 int *__restrict__ Ub_arr, int *__restrict__ flags,
                                                 int64_t *__restrict__ toff, int *__restrict__ rowstart,
-                                                int *__restrict__ slow) {
+                                                int *__restrict__ slow, int *__restrict__ bad_arr) {
     __shared__ long long s_part[2][32];
     __shared__ long long s_carry[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -44,10 +44,12 @@ __global__ void __launch_bounds__(1024) k0_prep(const int64_t *__restrict__ in_l
         long long tb = 0, ub = 0;
         if (b < B) {
             long long t = in_len[b], u = tgt_len[b];
-            if (t < 0 || t > T) { bad |= 1; t = t < 0 ? 0 : T; }
-            if (u < 0 || u > Umax) { bad |= 2; u = u < 0 ? 0 : Umax; }
+            int mybad = 0;
+            if (t < 0 || t > T) { mybad |= 1; t = t < 0 ? 0 : T; }
+            if (u < 0 || u > Umax) { mybad |= 2; u = u < 0 ? 0 : Umax; }
+            bad |= mybad;
             tb = t; ub = u;
-            Tb_arr[b] = (int)t; Ub_arr[b] = (int)u; flags[b] = 0; slow[b] = 0;
+            Tb_arr[b] = (int)t; Ub_arr[b] = (int)u; flags[b] = 0; slow[b] = 0; bad_arr[b] = mybad;
         }
         // block-wide inclusive scan of (tb, ub)
         long long st = tb, su = ub;
@@ -215,7 +217,8 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
               const int64_t *__restrict__ toff_arr, const int *__restrict__ rowstart,
               float *__restrict__ lp_lab, int *__restrict__ hdr, int B, int T, int V, int Lp, int blank,
               int nst, uint32_t slot_bytes, float *__restrict__ grad, int reduction, float inv_batch,
-              int *__restrict__ best, int zero_pad_here, int *__restrict__ slow, float lin_thr) {
+              int *__restrict__ best, int zero_pad_here, int *__restrict__ slow, float lin_thr,
+              int *__restrict__ bad_arr) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     griddep_wait();                                  // k0_prep's lengths / prefix sums
@@ -269,6 +272,9 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
                     long long c = idx < tnumel ? targets[idx] : -1;
                     if (c < 0 || c >= V || c == blank) {
                         atomicOr(&hdr[0], 4);
+                        // a label outside [0,V) poisons the utterance's nll / gradient with NaN (torch would read out of
+                        // bounds); label == blank is only reported: torch computes with it like with any other class
+                        if (c < 0 || c >= V) atomicOr(&bad_arr[cur_b], 4);
                         c = c < 0 ? 0 : (c >= V ? V - 1 : c);
                     }
                     cls = (int)c;
@@ -460,7 +466,7 @@ k3_grad(const float *__restrict__ logits, const int64_t *__restrict__ targets, i
         const int *__restrict__ flags, const int *__restrict__ rowstart, const float *__restrict__ gam,
         const float *__restrict__ grad_out, int64_t go_stride, int reduction, float inv_batch,
         float *__restrict__ grad, int B, int T, int V, int Lp, int blank, int zero_inf, int nst,
-        uint32_t slot_bytes, uint32_t stage_bytes) {
+        uint32_t slot_bytes, uint32_t stage_bytes, const int *__restrict__ bad_arr) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
     const int R = rowstart[B];
@@ -486,7 +492,7 @@ k3_grad(const float *__restrict__ logits, const int64_t *__restrict__ targets, i
             int issued = 0;
             auto issue = [&](int stg) {
                 const uint32_t dst = slot0 + stg * stage_bytes, bar = bar0 + 8 * stg;
-                if (zero_inf && flags[pc.b]) {
+                if (zero_inf && flags[pc.b] && !bad_arr[pc.b]) {
                     mbar_arrive(bar);                      // zeroed utterance: nothing to read
                 } else {
                     const size_t fr = (size_t)pc.b * T + pc.t;
@@ -509,8 +515,9 @@ k3_grad(const float *__restrict__ logits, const int64_t *__restrict__ targets, i
                     const int infeasible = flags[cur_b];
                     const float go = grad_out[go_stride ? (int64_t)cur_b * go_stride : 0];
                     g = go * (reduction == 1 ? inv_batch * __frcp_rn((float)(Ub > 1 ? Ub : 1)) : 1.f);
-                    zero_rows = infeasible && zero_inf;
-                    if (infeasible && !zero_inf) g = __int_as_float(0x7fc00000);   // torch: NaN frames
+                    const int isbad = bad_arr[cur_b];
+                    zero_rows = infeasible && zero_inf && !isbad;
+                    if ((infeasible && !zero_inf) || isbad) g = __int_as_float(0x7fc00000);   // torch: NaN frames
                     const int64_t toff = toff_arr[cur_b];
                     __syncthreads();   // previous utterance's patch reads are done
                     for (int k = tid; k <= Ub; k += NT) {
@@ -618,7 +625,8 @@ __global__ void __launch_bounds__(NT)
 k3p_patch(const int64_t *__restrict__ targets, int64_t tnumel, const int *__restrict__ Tb_arr,
           const int *__restrict__ Ub_arr, const int64_t *__restrict__ toff_arr, const int *__restrict__ flags,
           const int *__restrict__ rowstart, const float *__restrict__ gam, float *__restrict__ grad,
-          int reduction, float inv_batch, int B, int T, int V, int Lp, int blank, int zero_inf, float occ_skip) {
+          int reduction, float inv_batch, int B, int T, int V, int Lp, int blank, int zero_inf, float occ_skip,
+          const int *__restrict__ bad_arr) {
     extern __shared__ __align__(128) unsigned char smem[];
     int *pcls = (int *)smem;                  // [Lp] class of patch slot k (0 = blank, k>=1: label k-1)
     int *pnext = pcls + Lp;                   // [Lp] next slot with the same class, or -1
@@ -670,8 +678,9 @@ k3p_patch(const int64_t *__restrict__ targets, int64_t tnumel, const int *__rest
         if (!waited) { griddep_wait(); waited = true; }   // the lattice's occupancies and flags, the sweep's dense gradient
         // (coherent L2 loads for everything the lattice kernel wrote: this kernel may have started, and the SM's
         // non-coherent cache may have been primed, before those writes)
-        if (__ldcg(flags + b)) {               // no valid alignment
-            if (zero_inf) zero_span<NT>(gbase, (size_t)seg * V, tid);
+        const int isbad = __ldcg(bad_arr + b);   // (k0_prep / the sweep wrote it: complete before the lattice started)
+        if (__ldcg(flags + b) || isbad) {      // no valid alignment, or invalid lengths / labels (-> NaN)
+            if (zero_inf && !isbad) zero_span<NT>(gbase, (size_t)seg * V, tid);
             else fill_span<NT>(gbase, (size_t)seg * V, tid, __int_as_float(0x7fc00000));
         } else {
             const float *gf = gam + ((size_t)b * T + t0) * Lp;
@@ -725,7 +734,10 @@ __global__ void __launch_bounds__(256) k4_rescale(float *__restrict__ grad, cons
     const float gold = applied_in[b];
     if (blockIdx.x == 0 && threadIdx.x == 0) applied_out[b] = gnew;
     if (gnew == gold) return;
-    const float f = gnew / gold;
+    // A slab that was scaled by 0 cannot be rescaled: the caller must recompute it (ctcb200_backward).  The autograd op
+    // never gets here (it rescales only the unit-scale speculative gradient, once); a raw ABI caller that does gets NaN
+    // rather than a silently wrong gradient.
+    const float f = gold != 0.f ? gnew / gold : __int_as_float(0x7fc00000);
     float *p = grad + (size_t)b * T * V;
     const size_t n = (size_t)T * V;
     const size_t head = ((16 - ((uintptr_t)p & 15)) & 15) >> 2;

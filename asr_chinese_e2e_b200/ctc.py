@@ -23,7 +23,43 @@ import torch
 from . import _lib
 
 _RED = {"none": 0, "mean": 1, "sum": 2}
-_DEBUG = bool(int(os.environ.get("CTCB200_DEBUG", "0")))
+
+# Host-side developer knobs: read from the environment ONCE, at import; `configure()` changes them afterwards.
+_CFG = {
+    "debug": bool(int(os.environ.get("CTCB200_DEBUG", "0"))),        # read the device status word after every call (syncs)
+    "fused": bool(int(os.environ.get("CTCB200_FUSED", "1"))),        # gradient produced inside the forward call
+    "two_sweep": bool(int(os.environ.get("CTCB200_TWO_SWEEP", "1"))),
+    "split": float(os.environ.get("CTCB200_SPLIT", "1.0")),          # two-stream utterance split (lost: DESIGN.md 5)
+    "chunks": int(os.environ["CTCB200_CHUNKS"]) if "CTCB200_CHUNKS" in os.environ else None,
+    "lattice_log": False,                                            # CTCB200_FLAG_LATTICE_LOG on every call
+}
+
+
+def configure(**kw):
+    """Change a host-side developer knob (debug, fused, two_sweep, split, chunks, lattice_log).
+    Returns the previous values."""
+    old = {k: _CFG[k] for k in kw}
+    for k, v in kw.items():
+        if k not in _CFG:
+            raise KeyError(k)
+        _CFG[k] = v
+    return old
+
+
+def _validate_host(name, x, lo, hi):
+    """Lengths that are still on the host are checked for free, with F.ctc_loss's error behaviour (it raises);
+    device-resident ones are checked by the kernels, which poison the result with NaN (no host sync)."""
+    if torch.is_tensor(x):
+        if x.is_cuda or x.numel() == 0:
+            return
+        mn, mx = int(x.min()), int(x.max())
+    else:
+        seq = list(x)
+        if not seq:
+            return
+        mn, mx = int(min(seq)), int(max(seq))
+    if mn < lo or mx > hi:
+        raise ValueError(f"{name} must lie in [{lo}, {hi}] (got min {mn}, max {mx})")
 
 
 def _as_i64_cuda(x, device):
@@ -44,6 +80,12 @@ def _prepare(logits, targets, input_lengths, target_lengths, blank, max_target_l
         x = x.clone()
     B, T, V = x.shape
     dev = x.device
+    _validate_host("input_lengths", input_lengths, 0, T)
+    if torch.is_tensor(targets) and targets.dim() == 2:
+        _validate_host("target_lengths", target_lengths, 0, targets.shape[1])
+    if torch.is_tensor(targets) and not targets.is_cuda and targets.numel():
+        if int(targets.min()) < 0 or int(targets.max()) >= V:
+            raise ValueError(f"targets must lie in [0, {V})")
     il = _as_i64_cuda(input_lengths, dev)
     tl = _as_i64_cuda(target_lengths, dev)
     tg = _as_i64_cuda(targets, dev)
@@ -114,7 +156,7 @@ def _ones(dev, n):
 
 
 def _n_chunks(B, requested):
-    n = requested if requested is not None else int(os.environ.get("CTCB200_CHUNKS", "1"))
+    n = requested if requested is not None else (_CFG["chunks"] or 1)
     return max(1, min(int(n), B)) if B else 1
 
 
@@ -146,7 +188,7 @@ def _two_sweep_pipeline(ctx, L, x, tg, stride, il, tl, B, T, V, umax, blank, zi,
     doubles its time when it shares the memory system with a sweep), hence the default 1.0."""
     dev = x.device
     m = 4 // math.gcd(T * V, 4)                      # chunk starts must stay 16-byte aligned
-    split = float(os.environ.get("CTCB200_SPLIT", "1.0"))   # measured on B200: one chunk wins (profiles/), see DESIGN.md 5
+    split = _CFG["split"]                            # measured on B200: one chunk wins (profiles/), see DESIGN.md 5
     cut = int(round(B * split / m)) * m
     bounds = [0, B] if (B < 16 or cut <= 0 or cut >= B or stride == 0) else [0, cut, B]
     n_ch = len(bounds) - 1
@@ -188,15 +230,16 @@ def _two_sweep_pipeline(ctx, L, x, tg, stride, il, tl, B, T, V, umax, blank, zi,
             for c in range(n_ch):
                 main.wait_event(ev_l[c])
                 call(c, 4, main)
-        if _DEBUG:
+        if _CFG["debug"]:
             for c in range(n_ch):
                 _check_status(ws[ws_off[c]:], main.cuda_stream)
         if decode is not None:
             _decode_chunks(L, decode, tg, stride, [(bounds[c], bounds[c + 1] - bounds[c], ws.data_ptr() + ws_off[c],
                                                     ws_bytes[c]) for c in range(n_ch)], T, V, umax, blank, main, dev, B)
     ctx.cfg = (stride, B, T, V, umax, blank, zi, red, 0, 0, n_ch, inv_b, True)
-    ctx.applied = _ones(dev, B)
-    ctx.save_for_backward(grad)
+    ctx.chunk_map = [(bounds[c], bounds[c + 1] - bounds[c], ws_off[c], ws_bytes[c]) for c in range(n_ch)]
+    ctx.speculative_used = False
+    ctx.save_for_backward(grad, x, tg, ws)
     if reduction == "none":
         return nll
     if n_ch == 1:                                     # the lattice kernel already reduced (and scaled) the batch
@@ -219,14 +262,15 @@ class _CTCLossB200Fn(torch.autograd.Function):
         L = _lib.lib()
         need_grad = ctx.needs_input_grad[0]
         fused = bool(need_grad and fused)
-        two_sweep = bool(int(os.environ.get("CTCB200_TWO_SWEEP", "1")))
+        two_sweep = _CFG["two_sweep"]
         red = _RED[reduction]
-        zi = int(bool(zero_infinity)) | (2 if decode is not None else 0)   # bit 1: record per-frame argmax
+        zi = (int(bool(zero_infinity)) | (2 if decode is not None else 0)   # bit 1: record per-frame argmax
+              | (4 if _CFG["lattice_log"] else 0))                           # bit 2: log-space recursion everywhere
         inv_b = float(inv_batch) if inv_batch is not None else (1.0 / max(B, 1))
         dev = x.device
         nll = torch.empty(B, dtype=torch.float32, device=dev)
         grad = torch.empty_like(x) if fused else None
-        if fused and two_sweep and chunks is None and "CTCB200_CHUNKS" not in os.environ:
+        if fused and two_sweep and chunks is None and _CFG["chunks"] is None:
             out = _two_sweep_pipeline(ctx, L, x, tg, stride, il, tl, B, T, V, umax, int(blank), zi, red, inv_b,
                                       nll, grad, reduction, decode, lattice_event)
             return out
@@ -287,7 +331,7 @@ class _CTCLossB200Fn(torch.autograd.Function):
                     e_ = torch.cuda.Event()
                     e_.record(s_)
                     main.wait_event(e_)
-            if _DEBUG:
+            if _CFG["debug"]:
                 for c in range(n_ch):
                     _check_status(ws[c * ws_bytes:], main.cuda_stream)
             if decode is not None:
@@ -295,10 +339,12 @@ class _CTCLossB200Fn(torch.autograd.Function):
                                [(c * per, min((c + 1) * per, B) - c * per, ws.data_ptr() + c * ws_bytes, ws_bytes)
                                 for c in range(n_ch) if c * per < B], T, V, umax, int(blank), main, dev, B)
         ctx.cfg = (stride, B, T, V, umax, int(blank), zi, red, ws_bytes, per, n_ch, inv_b, fused)
+        ctx.chunk_map = [(c * per, min((c + 1) * per, B) - c * per, c * ws_bytes, ws_bytes)
+                         for c in range(n_ch) if c * per < B]
+        ctx.speculative_used = False
         if need_grad:
             if fused:
-                ctx.applied = _ones(dev, B)
-                ctx.save_for_backward(grad)
+                ctx.save_for_backward(grad, x, tg, ws)
             else:
                 ctx.save_for_backward(x, tg, ws)
         if reduction == "none":
@@ -313,32 +359,33 @@ class _CTCLossB200Fn(torch.autograd.Function):
         stride, B, T, V, umax, blank, zi, red, ws_bytes, per, n_ch, inv_b, fused = ctx.cfg
         go = grad_out.to(dtype=torch.float32).contiguous()
         L = _lib.lib()
-        if fused:
-            (grad,) = ctx.saved_tensors
+        if fused and not ctx.speculative_used:
+            # First backward of this graph: the forward call left the gradient for an upstream gradient of 1 in
+            # `grad`.  k4 compares the real upstream gradient with 1 on the device and exits without touching memory
+            # when they agree (loss.backward()), or scales the slab by it otherwise.  The buffer is handed to
+            # autograd here and never written again: a later backward of a retained graph recomputes (below).
+            grad = ctx.saved_tensors[0]
+            ctx.speculative_used = True
             with torch.cuda.device(grad.device):
                 stream = torch.cuda.current_stream().cuda_stream
-                applied_new = torch.empty_like(ctx.applied)
+                ones = _ones(grad.device, B)
+                scratch = torch.empty(B, dtype=torch.float32, device=grad.device)
                 _lib.check(L.ctcb200_rescale_grad(grad.data_ptr(), go.data_ptr(), 1 if red == 0 else 0,
-                                                  ctx.applied.data_ptr(), applied_new.data_ptr(), B, T, V, stream),
+                                                  ones.data_ptr(), scratch.data_ptr(), B, T, V, stream),
                            "ctcb200_rescale_grad")
-                ctx.applied = applied_new
             return (grad,) + (None,) * 12
-        x, tg, ws = ctx.saved_tensors
+        x, tg, ws = ctx.saved_tensors[-3:]
         grad = torch.empty_like(x)
         xs = x.element_size() * T * V
         gs = 4 if red == 0 else 0
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream().cuda_stream
-            for c in range(n_ch):
-                lo, hi = c * per, min((c + 1) * per, B)
-                n = hi - lo
-                if n <= 0:
-                    break
+            for lo, n, wo, wb in ctx.chunk_map:
                 tgp = tg.data_ptr() + (lo * stride * 8 if stride else 0)
                 _lib.check(L.ctcb200_backward(x.data_ptr() + lo * xs, tgp, stride, tg.numel() - lo * stride,
                                               go.data_ptr() + lo * gs, 1 if red == 0 else 0, red, inv_b, n, T, V,
                                               umax, blank, zi, grad.data_ptr() + lo * xs,
-                                              ws.data_ptr() + c * ws_bytes, ws_bytes, stream), "ctcb200_backward")
+                                              ws.data_ptr() + wo, wb, stream), "ctcb200_backward")
         return (grad,) + (None,) * 12
 
 
@@ -365,7 +412,7 @@ def ctc_loss_b200(logits, targets, input_lengths, target_lengths, blank: int = 0
     if reduction not in _RED:
         raise ValueError(f"reduction must be one of {list(_RED)}")
     if fused is None:
-        fused = bool(int(os.environ.get("CTCB200_FUSED", "1")))
+        fused = _CFG["fused"]
     if torch.is_tensor(targets) and targets.dim() == 1:
         chunks = 1
     ev = [lattice_event, False] if lattice_event is not None else None

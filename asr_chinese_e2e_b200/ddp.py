@@ -3,8 +3,10 @@
 Replaces ``Predictor/Bases/base_model.py:9-21`` (``Wrapper`` around ``nn.DataParallel``, commented out at
 ``main.py:80``): same constructor idea and the same attribute pass-through to the wrapped model, but every rank
 owns one GPU and its own DataLoader shard, gradients are averaged by DDP's bucketed NCCL all-reduce during
-``loss.backward()``, and the CTC branch uses ``sharded_ctc_loss`` semantics (1/B_global folded into the op, so
-no extra collective on the loss path).  ``torch.distributed`` is plumbing here, not a kernel of this repo.
+``loss.backward()``.  Because DDP AVERAGES, every rank's loss is normalised by its LOCAL batch:
+``JointCTCAttention.joint_loss`` passes inv_batch = w / B_local, and ``sharded_ctc_loss(grad_reduce='mean')``
+(the default) does the same while returning the global value.  ``torch.distributed`` is plumbing here, not a
+kernel of this repo.
 """
 import os
 
@@ -67,10 +69,14 @@ class DistributedWrapper(torch.nn.Module):
 
 def shard_batch(batch, rank, world_size):
     """This rank's contiguous slice of every batch-major tensor in a dict / Pack (equal shards, like the
-    reference's ``drop_last=True`` loader would hand each rank)."""
-    out = type(batch)() if not isinstance(batch, dict) else {}
+    reference's ``drop_last=True`` loader would hand each rank).  The container type is preserved (a ``Pack`` stays
+    a ``Pack``); a batch size that is not a multiple of world_size is an error rather than a silent drop."""
+    out = type(batch)()
     for k, v in batch.items():
         if torch.is_tensor(v) and v.dim() >= 1:
+            if v.shape[0] % world_size:
+                raise ValueError(f"batch dimension {v.shape[0]} of '{k}' is not a multiple of world_size {world_size} "
+                                 "(the reference's loader uses drop_last=True)")
             per = v.shape[0] // world_size
             v = v[rank * per:(rank + 1) * per]
         out[k] = v

@@ -25,6 +25,7 @@ import torch.nn.functional as F
 
 from .ce import attention_ce_b200
 from .ctc import ctc_loss_b200
+from .metrics import seq_cer_b200
 
 IGNORE_ID = 0   # PAD id of the reference vocab == CTC blank (Predictor/Utils/loss.py:5, vocab.py:10)
 
@@ -64,6 +65,29 @@ def edit_distance(a, b) -> int:
             cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
         prev = cur
     return prev[-1]
+
+
+def reference_cer(hyp_ids, gold_ids, pad: int = IGNORE_ID) -> float:
+    """Host restatement of the reference's ``cer`` (transformer_official.py:87-91): per utterance the Levenshtein
+    distance between the SPACE-JOINED strings of the non-PAD ids (vocab.py:74-78, score.py:4-13; every token is one
+    character, so the joined string is the symbol sequence t1 SP t2 ... tn), divided by the number of gold words
+    (``len(''.split(' ')) == 1``), times 100, averaged over the batch.  Used on CPU tensors and as the checker of the
+    device kernel (metrics.seq_cer_b200)."""
+    def joined(ids):
+        toks = [int(t) for t in ids if int(t) != pad]
+        out = []
+        for k, t in enumerate(toks):
+            if k:
+                out.append(-7)
+            out.append(t)
+        return out, max(len(toks), 1)
+    tot, n = 0.0, 0
+    for h, g in zip(hyp_ids, gold_ids):
+        hs, _ = joined(h)
+        gs, words = joined(g)
+        tot += edit_distance(hs, gs) / words
+        n += 1
+    return tot * 100.0 / max(n, 1)
 
 
 def attention_ce(pred, gold, smoothing: float = 0.0):
@@ -109,12 +133,14 @@ class JointCTCAttention:
     ctc_zero_infinity: bool = True
 
     def init_ctc(self, d_model: int, vocab_size: int, ctc_weight: float = 0.3, ctc_zero_infinity: bool = True,
-                 smoothing: float = 0.0, ctc_cer_on_device: bool = False):
+                 smoothing: float = 0.0, ctc_cer_on_device: bool = True):
         self.ctc_head = torch.nn.Linear(d_model, vocab_size)
         self.ctc_weight = float(ctc_weight)
         self.ctc_zero_infinity = bool(ctc_zero_infinity)
         self.att_smoothing = float(smoothing)
-        self.ctc_cer_on_device = bool(ctc_cer_on_device)   # adds a `ctc_cer` metric (greedy CTC, device-side)
+        # on CUDA batches: adds a `ctc_cer` metric (greedy CTC decode + edit distance of the same forward pass,
+        # device-side, no sync); the attention-branch `cer` is computed on the device either way
+        self.ctc_cer_on_device = bool(ctc_cer_on_device)
 
     # -- forward: encoder tap + CTC head, then the decoder exactly as the reference calls it --------
     def forward(self, input):
@@ -148,13 +174,15 @@ class JointCTCAttention:
     def cal_metrics(self, output, input):
         loss, ctc, att = self.joint_loss(output, input)
         assert not torch.isinf(loss)           # the reference's only numerical guard (transformer_official.py:88)
-        hyp = output.pred.argmax(-1)
-        cer = 0.0
-        for h, g in zip(hyp.tolist(), output.gold.tolist()):
-            g = [t for t in g if t != IGNORE_ID]
-            cer += edit_distance(h[: len(g)], g) / max(len(g), 1)
-        cer = cer * 100.0 / max(hyp.size(0), 1)
-        pack = Pack(loss=loss, cer=torch.tensor([cer]), ctc_loss=ctc.detach(), att_loss=att.detach())
+        # `cer` is the reference's metric (arg-max ids -> space-joined strings -> Levenshtein / #gold words,
+        # transformer_official.py:87-91).  On CUDA it is one kernel launch and the value stays on the device: the train
+        # step has no .tolist() / Python Levenshtein loop; Trainer11 reads it with .item() like every other metric.
+        hyp = output.pred.topk(1)[1].squeeze(-1)   # the reference's own op (ties in all-zero padded rows resolve alike)
+        if hyp.is_cuda:
+            cer = seq_cer_b200(hyp, output.gold, pad=IGNORE_ID, mode="string")
+        else:
+            cer = torch.tensor([reference_cer(hyp.tolist(), output.gold.tolist())])
+        pack = Pack(loss=loss, cer=cer, ctc_loss=ctc.detach(), att_loss=att.detach())
         dec = getattr(self, "_last_decode", None)
         if dec:   # CTC-branch CER of the same forward pass, computed entirely on the device (no sync here)
             tl = input.tgt_len.to(dec["edit_distance"].device).clamp(min=1).float()

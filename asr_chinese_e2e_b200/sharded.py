@@ -3,9 +3,15 @@
 Utterances are independent, so each rank runs the kernels on its own shard with no data-path
 collective.  The only exchange is ONE all-reduce of the 2-element buffer
 ``[sum_b nll_b / max(U_b,1), B_local]`` (NCCL over NVLink on GPUs, gloo in the CPU tests); the global
-'mean' loss is ``buf[0] / buf[1]``.  The returned tensor has the GLOBAL value and a LOCAL gradient:
-d loss / d logits_local = 1 / (B_global * U_b) * (softmax - occupancy), which is what a DDP
-all-reduce of parameter gradients (sum) then expects.  With equal shards (the reference's
+'mean' loss is ``buf[0] / buf[1]``.  The returned tensor has the GLOBAL value and a LOCAL gradient whose scale
+depends on how the caller combines parameter gradients across ranks (``grad_reduce``):
+
+  'mean' (default) -- ``DistributedDataParallel`` / ``ddp.DistributedWrapper`` AVERAGE parameter gradients, so each
+                      rank's gradient is that of its LOCAL mean, 1 / (B_local * U_b) * (softmax - occupancy); the
+                      average over ranks is then exactly the gradient of the global mean;
+  'sum'            -- a hand-rolled all-reduce(SUM) of gradients: 1 / (B_global * U_b) * (softmax - occupancy).
+
+With equal shards (the reference's
 drop_last=True) 1/B_global is known before the kernels run, so the op's upstream gradient is exactly 1
 and nothing waits on the collective; nothing ever syncs with the host.  The loss value is final after the
 lattice kernel, so the all-reduce is issued on a side stream behind an event recorded there and runs under
@@ -44,11 +50,12 @@ def _collective_stream(dev):
     return _SIDE[key]
 
 
-def combine_equal_shards(local_contrib: torch.Tensor, group=None, ready_event=None) -> torch.Tensor:
+def combine_equal_shards(local_contrib: torch.Tensor, group=None, ready_event=None, value_scale: float = 1.0) -> torch.Tensor:
     """Equal shard sizes (drop_last=True, as the reference's loader: data/data_loader/ai_shell_1.py:103):
-    local_contrib = sum_b nll_b/U_b / B_global is already this rank's share of the global mean, so the
-    upstream gradient of the op stays exactly 1 (no rescale sweep) and the collective is one all-reduce
-    of a single float, enqueued behind the kernels with no host sync."""
+    value_scale * sum over ranks of local_contrib is the global mean (value_scale = 1 when local_contrib is already
+    this rank's share sum_b nll_b/U_b / B_global, 1/world when it is the local mean), so the upstream gradient of
+    the op stays exactly 1 (no rescale sweep) and the collective is one all-reduce of a single float, enqueued
+    behind the kernels with no host sync."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local_contrib
     if ready_event is not None and local_contrib.is_cuda:
@@ -66,22 +73,35 @@ def combine_equal_shards(local_contrib: torch.Tensor, group=None, ready_event=No
     else:
         tot = local_contrib.detach().clone()
         dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    if value_scale != 1.0:
+        tot = tot * value_scale
     return local_contrib + (tot - local_contrib.detach())     # value: global mean; gradient: d/d local = 1
 
 
 def sharded_ctc_loss(logits, targets, input_lengths, target_lengths, blank: int = 0,
-                     zero_infinity: bool = False, group=None, max_target_length=None, equal_shards: bool = True):
-    """'mean'-reduced CTC loss over the GLOBAL batch; call on every rank with its own shard."""
+                     zero_infinity: bool = False, group=None, max_target_length=None, equal_shards: bool = True,
+                     grad_reduce: str = "mean"):
+    """'mean'-reduced CTC loss over the GLOBAL batch; call on every rank with its own shard.
+
+    grad_reduce: how the caller combines parameter gradients across ranks -- 'mean' (DistributedDataParallel,
+    ``DistributedWrapper``; the default) or 'sum' (see the module doc).  The returned VALUE is the global mean
+    either way."""
     from .ctc import ctc_loss_b200
+    if grad_reduce not in ("mean", "sum"):
+        raise ValueError("grad_reduce must be 'mean' or 'sum'")
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     B = logits.shape[0]
     if equal_shards:
         ev = torch.cuda.Event() if (world > 1 and logits.is_cuda) else None
+        gw = world if grad_reduce == "sum" else 1              # gradient normaliser: B_global or B_local
         local = ctc_loss_b200(logits, targets, input_lengths, target_lengths, blank=blank, reduction="mean",
-                              zero_infinity=zero_infinity, inv_batch=1.0 / max(world * B, 1),
+                              zero_infinity=zero_infinity, inv_batch=1.0 / max(gw * B, 1),
                               max_target_length=max_target_length, lattice_event=ev)
-        return combine_equal_shards(local, group, ready_event=ev)
+        return combine_equal_shards(local, group, ready_event=ev, value_scale=float(gw) / world)
     local_sum = ctc_loss_b200(logits, targets, input_lengths, target_lengths, blank=blank,
                               reduction="mean", zero_infinity=zero_infinity, inv_batch=1.0,
                               max_target_length=max_target_length)
-    return combine_sharded_mean(local_sum, B, group)
+    out = combine_sharded_mean(local_sum, B, group)
+    if grad_reduce == "mean" and world > 1:                    # same value, gradient scaled for an averaging reducer
+        out = out.detach() + (out - out.detach()) * world
+    return out

@@ -61,14 +61,17 @@ enum ctcb200_error {
     CTCB200_ERR_ALIGN = -5,     /* logits/grad base not 16-byte aligned, workspace not 256-byte aligned */
     CTCB200_ERR_REDUCTION = -6, /* unknown reduction code */
     CTCB200_ERR_WORKSPACE = -7, /* workspace_bytes smaller than ctcb200_workspace_bytes() */
-    CTCB200_ERR_NO_DEVICE = -8  /* no CUDA device / not an sm_100 device */
+    CTCB200_ERR_NO_DEVICE = -8, /* no CUDA device / not an sm_100 device */
+    CTCB200_ERR_OPTION = -9     /* ctcb200_set_option / _get_option: unknown name */
 };
 
 enum ctcb200_reduction { CTCB200_REDUCE_NONE = 0, CTCB200_REDUCE_MEAN = 1, CTCB200_REDUCE_SUM = 2 };
 
 /* The `zero_infinity` argument of the forward-type calls is a small bit field: bit 0 = zero_infinity,
- * bit 1 = also record the per-frame argmax class for ctcb200_greedy_decode (costs ~5 % of the sweep). */
-enum ctcb200_forward_flags { CTCB200_FLAG_ZERO_INFINITY = 1, CTCB200_FLAG_DECODE = 2 };
+ * bit 1 = also record the per-frame argmax class for ctcb200_greedy_decode (costs ~5 % of the sweep),
+ * bit 2 = run the log-space alpha/beta recursion for every utterance (the algorithm BASELINE.json's north_star
+ *         names; by default it is the fallback of the faster linear-domain recursion). */
+enum ctcb200_forward_flags { CTCB200_FLAG_ZERO_INFINITY = 1, CTCB200_FLAG_DECODE = 2, CTCB200_FLAG_LATTICE_LOG = 4 };
 
 /* bits of the device status word */
 enum ctcb200_status_bits {
@@ -79,6 +82,12 @@ enum ctcb200_status_bits {
 
 int ctcb200_version(void);
 const char *ctcb200_strerror(int code);
+
+/* Developer tunables (launch shapes, experiment switches; DESIGN.md section 7 lists the names).  Each is read from
+ * its CTCB200_* environment variable once, when the library is loaded; afterwards these two calls are the only way
+ * to change or read one.  Process-wide, not synchronised: set them before issuing work from several threads. */
+int ctcb200_set_option(const char *name, int value);
+int ctcb200_get_option(const char *name, int *value);
 
 /* Host-only arithmetic (no CUDA call): bytes of workspace the calls below need. */
 int ctcb200_workspace_bytes(int B, int T, int V, int Umax, size_t *out_bytes);
@@ -151,7 +160,8 @@ int ctcb200_loss_grad_stages(int stages, const float *logits, const int64_t *tar
  * real upstream gradient) and fix the result up later: this multiplies utterance b's gradient slab
  * in place by grad_out[b*stride] / applied_in[b] and records grad_out in applied_out[b].  When the
  * two are equal (loss.backward() with an upstream gradient of 1) the kernel exits without touching
- * memory, so the usual cost is one empty launch instead of a third sweep. */
+ * memory, so the usual cost is one empty launch instead of a third sweep.  applied_in[b] == 0 with a different
+ * grad_out cannot be rescaled (the slab holds zeros): the slab becomes NaN -- recompute it with ctcb200_backward. */
 int ctcb200_rescale_grad(float *grad_logits, const float *grad_out, int64_t grad_out_stride,
                          const float *applied_in, float *applied_out, int B, int T, int V,
                          ctcb200_stream_t stream);
@@ -167,6 +177,17 @@ int ctcb200_greedy_decode(const int64_t *targets, int64_t targets_stride, int64_
                           int B, int T, int V, int Umax, int blank, const void *workspace,
                           size_t workspace_bytes, int *edit_out, int *hyp_len_out, int64_t *hyp_out,
                           ctcb200_stream_t stream);
+
+/* The reference's `cer` metric on the device (cal_metrics, transformer_official.py:87-91 ->
+ * Vocab.convert_id2str, vocab.py:74-78 -> calculate_cer, Predictor/Utils/score.py:4-13): per row b the edit distance
+ * between hyp[b, 0..L) and gold[b, 0..L) (int64 id matrices with the given row strides), ids == pad dropped.
+ *   mode 0: token-level Levenshtein distance;
+ *   mode 1: distance between the space-joined strings (what python-Levenshtein returns for the reference's
+ *           single-character tokens): insertions / deletions of a token also cost its separator.
+ * edit_out[B]; words_out[B] = max(#gold tokens, 1) = len(gold_string.split(' ')), the reference's denominator.
+ * L <= 512 (mode 1) / 1024 (mode 0). */
+int ctcb200_edit_distance(const int64_t *hyp, int64_t hyp_stride, const int64_t *gold, int64_t gold_stride, int B,
+                          int L, int pad, int mode, int *edit_out, int *words_out, ctcb200_stream_t stream);
 
 /* Attention-branch loss on the same sweep machinery: cross-entropy with optional label
  * smoothing over pred[rows, V] logits, rows whose gold == ignore_index skipped -- the reference's

@@ -85,9 +85,9 @@ class _Toy(torch.nn.Module):
     def forward(self, x):
         return self.lin(x)
 
-    def iterate(self, x, y, world):
+    def iterate(self, x, y):
         out = self(x)                                            # through DDP when wrapped
-        loss = ((out - y) ** 2).sum() / (x.shape[0] * world)    # 1/B_global folded in, like sharded_ctc_loss
+        loss = ((out - y) ** 2).sum() / x.shape[0]              # LOCAL mean: DDP averages the gradients over ranks
         loss.backward()
         return loss.detach()
 
@@ -101,15 +101,54 @@ def _worker(rank, world, port, q):
     model = DistributedWrapper(_Toy(), dev)
     assert model.tag == "toy" and isinstance(model.module, _Toy)          # attribute pass-through
     g = torch.Generator().manual_seed(1)
-    batch = {"x": torch.randn(6, 4, generator=g), "y": torch.randn(6, 3, generator=g), "note": "kept"}
+    from asr_chinese_e2e_b200 import Pack
+    batch = Pack(x=torch.randn(6, 4, generator=g), y=torch.randn(6, 3, generator=g), note="kept")
     mine = shard_batch(batch, rank, world)
-    assert mine["x"].shape[0] == 3 and mine["note"] == "kept"
-    model.iterate(mine["x"], mine["y"], world)
-    # DDP averages gradients over ranks; with 1/B_global folded into each rank's loss the SUM is the full-batch
-    # gradient, i.e. world * averaged
-    q.put((rank, (model.module.lin.weight.grad * world).tolist()))     # plain lists: no fd passing after exit
+    assert isinstance(mine, Pack) and mine.x.shape[0] == 3 and mine.note == "kept"      # container type preserved
+    try:
+        shard_batch({"x": torch.zeros(5, 1)}, rank, world)
+        raise AssertionError("a ragged batch must not be dropped silently")
+    except ValueError:
+        pass
+    model.iterate(mine.x, mine.y)
+    # DDP averages gradients over ranks: with every rank's loss normalised by its LOCAL batch the averaged gradient
+    # IS the full-batch-mean gradient -- no compensation factor
+    q.put((rank, "toy", model.module.lin.weight.grad.tolist()))     # plain lists: no fd passing after exit
+
+    # the documented recipe end to end: DistributedWrapper + sharded_ctc_loss(grad_reduce='mean') must give the
+    # parameter gradient of the un-sharded global-mean CTC loss (the oracle stands in for the CUDA op on CPU)
+    import asr_chinese_e2e_b200.ctc as ctc_mod
+    from asr_chinese_e2e_b200.sharded import sharded_ctc_loss
+    from test_host_logic import oracle_ctc
+    ctc_mod.ctc_loss_b200 = oracle_ctc
+    head = DistributedWrapper(_Head(), dev)
+    c = _ctc_case()
+    sl = slice(rank * 3, rank * 3 + 3)
+    for mode in ("mean", "sum"):
+        head.module.zero_grad()
+        loss = sharded_ctc_loss(head(c["enc"][sl]), c["targets"][sl], c["input_lengths"][sl], c["target_lengths"][sl],
+                                grad_reduce=mode)
+        loss.backward()
+        q.put((rank, mode, (loss.item(), head.module.lin.weight.grad.tolist())))
     dist.barrier()
     dist.destroy_process_group()
+
+
+class _Head(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(3)
+        self.lin = torch.nn.Linear(5, 11)
+
+    def forward(self, enc):
+        return self.lin(enc)
+
+
+def _ctc_case():
+    g = torch.Generator().manual_seed(7)
+    tl = torch.tensor([3, 2, 4, 1, 3, 2])
+    return dict(enc=torch.randn(6, 9, 5, generator=g), input_lengths=torch.tensor([9, 8, 9, 5, 7, 9]), target_lengths=tl,
+                targets=torch.randint(1, 11, (6, 4), generator=g) * (torch.arange(4)[None] < tl[:, None]))
 
 
 def test_distributed_wrapper_gloo_world2():
@@ -118,14 +157,24 @@ def test_distributed_wrapper_gloo_world2():
     port = 31500 + os.getpid() % 2000
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     [p.start() for p in procs]
-    res = sorted([q.get(timeout=180) for _ in range(2)], key=lambda r: r[0])
+    res = [q.get(timeout=180) for _ in range(6)]
     [p.join(60) for p in procs]
     ref = _Toy()
     g = torch.Generator().manual_seed(1)
     x, y = torch.randn(6, 4, generator=g), torch.randn(6, 3, generator=g)
     (((ref(x) - y) ** 2).sum() / 6).backward()
-    for _, grad in res:
+    for _, _, grad in [r for r in res if r[1] == "toy"]:
         assert torch.allclose(torch.tensor(grad), ref.lin.weight.grad, atol=1e-6)
+    import torch.nn.functional as F
+    head, c = _Head(), _ctc_case()
+    full = F.ctc_loss(F.log_softmax(head(c["enc"]), -1).transpose(0, 1), c["targets"], c["input_lengths"],
+                      c["target_lengths"], reduction="mean")
+    full.backward()
+    for _, mode, (loss, grad) in [r for r in res if r[1] in ("mean", "sum")]:
+        assert abs(loss - full.item()) < 1e-5 * abs(full.item()), mode               # global value on every rank
+        # DDP averaged the gradients: 'mean' reproduces the global-mean gradient, 'sum' is world times too small
+        scale = 1.0 if mode == "mean" else 2.0
+        assert torch.allclose(torch.tensor(grad) * scale, head.lin.weight.grad, atol=1e-6), mode
 
 
 def test_wrapper_without_process_group_is_transparent():
