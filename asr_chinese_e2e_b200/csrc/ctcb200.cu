@@ -155,7 +155,8 @@ cudaError_t launch_k1x(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
     }
     return launch_pdl(0, k1_lse_gather<NT, MAXC, EXACT, FUSED, DIRECT>, dim3(c.grid), dim3(NT), c.smem, s, a.logits, a.targets,
                       a.tnumel, a.Tb, a.Ub, a.toff, a.rowstart, a.lp_lab, a.hdr, a.B, a.T, a.V, a.Lp, a.blank, c.nst,
-                      c.slot_bytes, a.grad, a.reduction, a.inv_batch, a.best, a.zero_pad_here, a.slow, a.lin_thr, a.bad);
+                      c.slot_bytes, a.grad, a.reduction, a.inv_batch, a.best, a.zero_pad_here, a.slow, a.lin_thr, a.bad,
+                      (FUSED && MAXC <= 32) ? opt(OPT_LABEL_KEEP_L2) : 0);
 }
 template <int NT, int MAXC, bool EXACT>
 cudaError_t launch_k1(const StreamCfg &c, cudaStream_t s, const K1Args &a) {

@@ -218,7 +218,7 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
               float *__restrict__ lp_lab, int *__restrict__ hdr, int B, int T, int V, int Lp, int blank,
               int nst, uint32_t slot_bytes, float *__restrict__ grad, int reduction, float inv_batch,
               int *__restrict__ best, int zero_pad_here, int *__restrict__ slow, float lin_thr,
-              int *__restrict__ bad_arr) {
+              int *__restrict__ bad_arr, int keep_l2) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     griddep_wait();                                  // k0_prep's lengths / prefix sums
@@ -255,6 +255,7 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
 
     int stage = 0, cur_b = -1;
     uint32_t parity = 0;
+    uint32_t lmask[4] = {0u, 0u, 0u, 0u};
     float g = 0.f;             // FUSED: speculative gradient scale of the current utterance (upstream gradient 1)
     for (int i = 0; i < nrows; ++i) {
         if (cc.b != cur_b) {   // block-uniform: (re)load the utterance's class ids
@@ -282,6 +283,22 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
                 cls_s[k] = cls;
             }
             __syncthreads();
+            if (FUSED && keep_l2) {
+                // which of this thread's gradient chunks hold a class of the utterance (blank or a label), for each of
+                // the four possible misalignments of a row: those chunks are revisited by the sparse patch kernel and
+                // are stored with an evict_last hint so that they may still be in L2 then
+#pragma unroll
+                for (int h = 0; h < 4; ++h) lmask[h] = 0u;
+                for (int k = 0; k < Lp; ++k) {
+                    const int c = cls_s[k];
+                    if (c < 0) continue;
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const int q = ((h + c) >> 2) - 1 - tid;       // chunk index relative to this thread's first chunk
+                        if (q >= 0 && q % NT == 0 && q / NT < MAXC) lmask[h] |= 1u << (q / NT);
+                    }
+                }
+            }
         }
         if (!DIRECT) mbar_wait(bar0 + 8 * stage, parity);
         const float *grow = logits + ((size_t)cc.b * T + cc.t) * V;
@@ -434,11 +451,13 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
             const float sc = g * __frcp_rn(tot);           // softmax = 2^(x-max) / sum: no lse rounding involved
             float *orow = grad + ((size_t)cc.b * T + cc.t) * V;
             float4 *g4 = (float4 *)((uintptr_t)orow & ~(uintptr_t)15);
+            const uint32_t lm = head == 0 ? lmask[0] : (head == 1 ? lmask[1] : (head == 2 ? lmask[2] : lmask[3]));
 #pragma unroll
             for (int k = 0; k < MAXC; ++k) {
                 const int c = 1 + tid + k * NT;
                 if ((EXACT && k < MAXC - 1) || c <= nch - 2)
-                    stg_v4_hint(g4 + c, make_float4(v[k].x * sc, v[k].y * sc, v[k].z * sc, v[k].w * sc), kEvictFirst);
+                    stg_v4_hint(g4 + c, make_float4(v[k].x * sc, v[k].y * sc, v[k].z * sc, v[k].w * sc),
+                                ((lm >> k) & 1u) ? kEvictLast : kEvictFirst);
             }
             if (tid == 0 || (tid == 1 && nch > 1)) {       // edge chunks: scalar stores inside the row
                 const int c = tid == 0 ? 0 : nch - 1;

@@ -14,7 +14,8 @@ from .ctc import _RED, _prepare
 
 def time_stages(logits, targets, input_lengths, target_lengths, blank=0, reduction="mean",
                 zero_infinity=False, iters=10, warmup=3):
-    """Returns dict(sweep_ms=[...], rest_ms=[...]) with one entry per timed iteration."""
+    """Returns dict(sweep_ms=[...], rest_ms=[...]) with one entry per timed iteration, and lattice_stats =
+    [utterances that ran the log-space recursion, of which: underflowed in the linear domain] of the last call."""
     x, tg, stride, il, tl, B, T, V, umax = _prepare(logits.detach(), targets, input_lengths, target_lengths,
                                                     blank, None)
     L = _lib.lib()
@@ -23,7 +24,8 @@ def time_stages(logits, targets, input_lengths, target_lengths, blank=0, reducti
     nll = torch.empty(B, device=x.device)
     sums = torch.zeros(4, device=x.device)
     grad = torch.empty_like(x)
-    out = {"sweep_ms": [], "rest_ms": []}
+    import ctypes
+    out = {"sweep_ms": [], "rest_ms": [], "lattice_stats": [0, 0]}
     with torch.cuda.device(x.device):
         st = torch.cuda.current_stream()
         for i in range(warmup + iters):
@@ -40,4 +42,7 @@ def time_stages(logits, targets, input_lengths, target_lengths, blank=0, reducti
             if i >= warmup:
                 out["sweep_ms"].append(e0.elapsed_time(e1))
                 out["rest_ms"].append(e1.elapsed_time(e2))
+        stats = (ctypes.c_int * 2)()
+        _lib.check(L.ctcb200_read_lattice_stats(ws.data_ptr(), stats, st.cuda_stream), "ctcb200_read_lattice_stats")
+        out["lattice_stats"] = [int(stats[0]), int(stats[1])]
     return out

@@ -3,23 +3,32 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--lengths var|full]
 
-A "step" is one pass of the hot path over one batch: prep + fused log-softmax/label-gather sweep +
-alpha/beta lattice + fused gradient sweep (4 kernel launches), producing the 'mean' loss and the
-gradient w.r.t. the [B,T,V] logits.  Workload at every N: BASELINE.json configs[1] per GPU
-(B=256, T=400, V=4234, U<=50, variable lengths with padding, reduction=mean) -- weak scaling,
-batch sharded by utterance, one NCCL all-reduce of [sum_b nll_b/U_b, B_local] per step.
+A "step" is one pass of the hot path over one batch through the public op (``loss = ctc_loss_b200(...)``,
+``loss.backward()``): prep + fused log-softmax/label-gather/dense-gradient sweep + alpha/beta lattice + sparse
+occupancy patch (+ one empty rescale launch), producing the 'mean' loss and the gradient w.r.t. the [B,T,V] logits.
+Workload at every N: BASELINE.json configs[1] per GPU (B=256, T=400, V=4234, U<=50, variable lengths with padding,
+reduction=mean) -- weak scaling, batch sharded by utterance, one all-reduce of a single float per step.
 
-One JSON line on stdout (rank 0).  `value` = whole-job utterances/s with the logits resident in
-HBM; `e2e` = the same metric through the host-buffer API (pinned host logits in, gradient + loss
-back to pinned host memory, copies inside the timed region); `roofline` = the dominant kernel
-(k3_grad) against the measured HBM peak; `cpu_baseline` = torch's CPU ctc_loss path on a bounded
-sample of the same batch, timed on this box's host cores.
+One JSON line on stdout (rank 0):
+  value         whole-job utterances/s with the logits resident in HBM (CUDA events, max over ranks)
+  e2e           the same metric through the host-buffer API (pinned host logits in, gradient + nll back to pinned
+                host memory, copies inside the timed region)
+  roofline      the dominant kernel, k1_lse_gather<FUSED> (the fused sweep), timed live with CUDA events on the
+                launching stream against the measured HBM peak; roofline_step = whole step
+  parity        the step's nll / gradient against the CPU oracle (torch's CPU ctc_loss), checked in this very run
+  cpu_baseline  torch's CPU log_softmax + ctc_loss + backward on the full batch (median; + a 1-thread figure)
+  configs       driver-visible sub-records: C2 full lengths, C2 with sharp (trained-like) posteriors, C4 long
+                utterances, C5 joint step with the 12-layer encoder -- each with ms/step, roofline fractions and the
+                lattice kernel's path counters
+  comm          (N > 1) what the single collective costs: step time with and without it
+``--impl reference`` times the reference arm: torch's CPU op on this box's host cores (rank 0 only).
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import platform
 import statistics
 import subprocess
 import sys
@@ -33,6 +42,7 @@ B_, T_, V_, U_ = 256, 400, 4234, 50
 SEED = 1002
 METRIC = "ctc_loss_grad_utterances_per_s"
 UNIT = "utt/s"
+REL_LOSS, ABS_GRAD = 1e-5, 1e-4
 
 
 def parse():
@@ -44,15 +54,17 @@ def parse():
     ap.add_argument("--lengths", default="var", choices=["var", "full"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=64, help="utterances in the CPU-baseline sample")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C2-full / C2-D2 / C4 / C5 sub-records")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--same-seed", action="store_true", help="N>1 experiment: every rank gets rank 0's batch")
     ap.add_argument("--vocab", type=int, default=V_, help="developer experiments only (default = BASELINE V)")
     ap.add_argument("--shape", default=None, help="developer experiments only: B,T,U (default = BASELINE C2 256,400,50)")
     return ap.parse_args()
 
 
-def make_batch(rank, lengths):
+def make_batch(rank, lengths, dist="D1"):
     from oracle.synth import make_case   # input generator only (seeded, CPU); not on the product path
-    return make_case(B_, T_, V_, U_, SEED + rank, dist="D1", full_lengths=(lengths == "full"))
+    return make_case(B_, T_, V_, U_, SEED + rank, dist=dist, full_lengths=(lengths == "full"))
 
 
 def peaks():
@@ -60,6 +72,16 @@ def peaks():
     if os.path.exists(p):
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return platform.processor() or "unknown"
 
 
 class ClockSampler:
@@ -126,13 +148,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
-def cpu_reference_line(args, c, steps, warmup):
-    """torch CPU F.log_softmax + F.ctc_loss + backward on a bounded sample (first n utterances)."""
+# ------------------------------------------------------------------------------------------------------------
+# CPU reference (the oracle / reference arm): torch CPU F.log_softmax + F.ctc_loss + backward
+# ------------------------------------------------------------------------------------------------------------
+def time_cpu(c, n, steps, warmup, threads):
     import torch
     from oracle.torch_ref import ref_step
-    n = min(args.cpu_sample, B_)
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    torch.set_num_threads(threads)
     x = c["logits"][:n].clone().requires_grad_(True)
     tg, il, tl = c["targets"][:n], c["input_lengths"][:n], c["target_lengths"][:n]
     for _ in range(warmup):
@@ -142,12 +164,28 @@ def cpu_reference_line(args, c, steps, warmup):
         t0 = time.perf_counter()
         ref_step(x, tg, il, tl)
         ts.append(time.perf_counter() - t0)
-    ms = 1e3 * sum(ts) / len(ts)
-    return {"value": n / (ms / 1e3), "unit": UNIT, "cores": cores, "kind": "reference",
-            "sample": f"first {n} utterances of the C2 batch (T={T_}, V={V_}, U<={U_}, lengths={args.lengths}), "
-                      f"torch {torch.__version__} CPU F.log_softmax+F.ctc_loss(mean)+backward fp32, "
-                      f"{warmup} warm-up + {steps} timed, mean",
-            "ms_per_step": ms, "threads": torch.get_num_threads()}
+    return ts
+
+
+def cpu_reference_line(args, c, steps, warmup, one_thread=True):
+    """full batch, all host threads, `warmup` warm-up + `steps` timed, MEDIAN; plus a
+    1-thread figure on a bounded 16-utterance sample."""
+    import torch
+    cores = os.cpu_count() or 1
+    ts = time_cpu(c, B_, steps, warmup, cores)
+    med = statistics.median(ts)
+    out = {"value": B_ / med, "unit": UNIT, "cores": cores, "kind": "reference", "cpu_model": cpu_model(),
+           "sample": f"the full C2 batch ({B_} utterances, T={T_}, V={V_}, U<={U_}, lengths={args.lengths}), "
+                     f"torch {torch.__version__} CPU F.log_softmax+F.ctc_loss(mean)+backward fp32, "
+                     f"{warmup} warm-up + {steps} timed, median",
+           "ms_per_step": 1e3 * med, "ms_per_step_mean": 1e3 * sum(ts) / len(ts), "threads": cores}
+    if one_thread:
+        n1 = min(16, B_)
+        t1 = time_cpu(c, n1, 2, 1, 1)
+        torch.set_num_threads(cores)
+        out["one_thread"] = {"value": n1 / statistics.median(t1), "unit": UNIT, "threads": 1,
+                             "sample": f"first {n1} utterances of the same batch, 1 warm-up + 2 timed, median"}
+    return out
 
 
 def run_reference(args):
@@ -155,13 +193,13 @@ def run_reference(args):
     if rank != 0:
         return
     c = make_batch(0, args.lengths)
-    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
-    cb = cpu_reference_line(args, c, steps, warmup)
+    steps, warmup = max(1, min(args.steps, 60)), max(1, min(args.warmup, 10))     # ~0.5 s per step on 16 cores
+    cb = cpu_reference_line(args, c, steps, warmup, one_thread=False)
     line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": workload_cfg(args, 1),
-            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -174,6 +212,147 @@ def workload_cfg(args, n):
             "global_batch": B_ * n, "lengths": args.lengths, "seed": SEED,
             "parallelism": f"batch-sharded x{n}, 1 all-reduce of 1 float/step" if n > 1 else "single GPU",
             "l2_policy": "inputs (1.73 GB logits + 1.73 GB grad per step) exceed the 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# helpers of the b200 arm
+# ------------------------------------------------------------------------------------------------------------
+def time_steps(torch, step, K, W):
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / K, out
+
+
+def parity_check(torch, c, nll_gpu, grad_gpu, n, zero_infinity=False, inv_batch=None):
+    """The first n utterances of the batch against the CPU oracle: per-utterance nll (relative) and the
+    'mean' gradient (absolute).  Infeasible utterances are compared by class."""
+    from oracle.torch_ref import ref_ctc
+    B = c["logits"].shape[0]
+    sub = {k: v[:n] for k, v in c.items()}
+    ref_nll, _ = ref_ctc(sub["logits"], sub["targets"], sub["input_lengths"], sub["target_lengths"], reduction="none",
+                         zero_infinity=zero_infinity, want_grad=False)
+    go = (inv_batch if inv_batch is not None else 1.0 / B) / sub["target_lengths"].clamp(min=1).float()
+    _, ref_g = ref_ctc(sub["logits"], sub["targets"], sub["input_lengths"], sub["target_lengths"], reduction="none",
+                       zero_infinity=zero_infinity, grad_output=go)
+    nll = nll_gpu[:n].detach().float().cpu()
+    fin = torch.isfinite(ref_nll)
+    same_class = bool(torch.equal(torch.isinf(nll), torch.isinf(ref_nll)))
+    rel = ((nll[fin] - ref_nll[fin]).abs() / ref_nll[fin].abs().clamp(min=1.0)).max().item() if fin.any() else 0.0
+    g = grad_gpu[:n].detach().cpu()
+    ok = ~torch.isnan(ref_g)
+    nan_same = bool(torch.equal(torch.isnan(g), torch.isnan(ref_g)))
+    gerr = (g[ok] - ref_g[ok]).abs().max().item() if ok.any() else 0.0
+    return {"nll_rel_max": rel, "grad_abs_max": gerr, "n_utts": int(n), "tol": {"nll_rel": REL_LOSS, "grad_abs": ABS_GRAD},
+            "oracle": "torch CPU F.log_softmax + F.ctc_loss (oracle/torch_ref.py), same inputs",
+            "pass": bool(rel <= REL_LOSS and gerr <= ABS_GRAD and same_class and nan_same)}
+
+
+def sub_record(torch, name, c, zero_infinity, K, peak, parity_n, note):
+    """One driver-visible sub-record: step time of the public op on another configuration + roofline fractions +
+    the lattice kernel's path counters + a parity gate on a bounded sample."""
+    from asr_chinese_e2e_b200 import ctc_loss_b200
+    from asr_chinese_e2e_b200.profiling import time_stages
+    dev = torch.device("cuda", torch.cuda.current_device())
+    x = c["logits"].to(dev).requires_grad_(True)
+    tg, il, tl = c["targets"].to(dev), c["input_lengths"].to(dev), c["target_lengths"].to(dev)
+    B, T, V = x.shape
+
+    def step():
+        x.grad = None
+        loss = ctc_loss_b200(x, tg, il, tl, blank=0, reduction="mean", zero_infinity=zero_infinity)
+        loss.backward()
+        return loss
+    ms, loss = time_steps(torch, step, K, 3)
+    st = time_stages(x, tg, il, tl, reduction="mean", zero_infinity=zero_infinity, iters=min(K, 20), warmup=2)
+    sum_T = int(c["input_lengths"].sum())
+    b2, b3 = 4 * V * (sum_T + B * T), 4 * V * (2 * sum_T + B * T)
+    rec = {"workload": note, "B": B, "T": T, "V": V, "value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms,
+           "loss": float(loss.item()), "steps": K,
+           "algorithmic_bytes_2sweep": b2, "frac_2sweep": b2 / (ms / 1e3) / 1e9 / peak,
+           "frac_3sweep": b3 / (ms / 1e3) / 1e9 / peak,
+           "sweep_ms": statistics.mean(st["sweep_ms"]), "lattice_plus_patch_ms": statistics.mean(st["rest_ms"]),
+           "sweep_frac": b2 / (statistics.mean(st["sweep_ms"]) / 1e3) / 1e9 / peak,
+           "lattice_stats": {"utterances": B, "log_space": st["lattice_stats"][0],
+                             "of_which_underflowed_in_linear_domain": st["lattice_stats"][1]}}
+    if parity_n:
+        nll = ctc_loss_b200(x.detach(), tg, il, tl, reduction="none", zero_infinity=zero_infinity)
+        step()
+        rec["parity"] = parity_check(torch, c, nll, x.grad, parity_n, zero_infinity)
+    del x
+    torch.cuda.empty_cache()
+    return rec
+
+
+def c5_record(torch, dist, world, rank, dev, K=5):
+    """BASELINE config C5: joint CTC/attention step with the reference's 12-layer encoder architecture (PyTorch,
+    fp32) feeding the CTC kernels, B=128/GPU, T=400; under DistributedDataParallel (DistributedWrapper) at N>1.
+    Reports the step time and the CTC branch's share of it (step with the CTC branch minus step without)."""
+    import torch.nn.functional as F
+    from asr_chinese_e2e_b200 import DistributedWrapper, JointCTCAttention, Pack
+    from asr_chinese_e2e_b200.speech_encoder import SpeechEncoder
+    from oracle.synth import make_lengths, make_targets
+    B, T, V, U, D = 128, 400, V_, 50, 512
+
+    class Dec(torch.nn.Module):                 # a light attention-branch stand-in (the decoder body is outside this path)
+        def __init__(self):
+            super().__init__()
+            self.emb, self.out = torch.nn.Embedding(V, D), torch.nn.Linear(D, V)
+
+        def forward(self, tgt, enc, lens):
+            n = tgt.size(0)
+            ys = torch.cat([torch.full((n, 1), 2, device=tgt.device), tgt], 1)
+            gold = torch.cat([tgt, torch.zeros(n, 1, dtype=torch.long, device=tgt.device)], 1)
+            gold[torch.arange(n, device=tgt.device), lens] = 3
+            return self.out(self.emb(ys) + enc.mean(1, keepdim=True)), gold
+
+    class Model(JointCTCAttention, torch.nn.Module):
+        def __init__(self):
+            torch.nn.Module.__init__(self)
+            self.encoder, self.decoder = SpeechEncoder(n_layers=12, dropout=0.1), Dec()
+            self.init_ctc(D, V, ctc_weight=0.3, ctc_zero_infinity=True)
+            self.use_ctc = True
+
+        def joint_loss(self, output, input):
+            if self.use_ctc:
+                return JointCTCAttention.joint_loss(self, output, input)
+            att = F.cross_entropy(output.pred.reshape(-1, V), output.gold.reshape(-1), ignore_index=0)
+            att = att + 0.0 * output.ctc_logits.sum()          # keep the head in the graph (same GEMMs, no CTC)
+            return att, att.detach(), att
+
+    torch.manual_seed(1005)
+    g = torch.Generator().manual_seed(1005 + rank)
+    tg, tl = make_targets(B, U, V, g)
+    il = make_lengths(B, T, g)
+    batch = Pack(wave=torch.randn(B, T, 320, generator=g), wave_len=il, tgt_for_input=tg, tgt_len=tl).to(dev)
+    model = DistributedWrapper(Model(), dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.98), eps=1e-9)
+    res = {}
+    for kind in ("with_ctc", "without_ctc"):
+        model.module.use_ctc = kind == "with_ctc"
+        ms, met = time_steps(torch, lambda: model.iterate(batch, optimizer=opt, is_train=True)[0], K, 2)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        res[kind] = ms
+        if kind == "with_ctc":
+            loss = float(met.loss.item())
+    del model, opt, batch
+    torch.cuda.empty_cache()
+    return {"workload": f"C5: joint CTC/attention step (ctc_weight 0.3), 12-layer encoder (d_model 512, 8 heads, FFN 1024) "
+                        f"in PyTorch fp32 + CTC head + this repo's CTC / CE / CER kernels, B={B}/GPU, T={T}, V={V}; "
+                        + ("DistributedDataParallel via DistributedWrapper" if world > 1 else "single GPU"),
+            "ms_per_step": res["with_ctc"], "ms_per_step_without_ctc_branch": res["without_ctc"],
+            "ctc_branch_ms": res["with_ctc"] - res["without_ctc"],
+            "ctc_share": (res["with_ctc"] - res["without_ctc"]) / res["with_ctc"],
+            "value": world * B / (res["with_ctc"] / 1e3), "unit": UNIT, "steps": K, "loss": loss}
 
 
 def main():
@@ -201,16 +380,16 @@ def main():
     _lib.lib()                                                  # fail loudly if the .so is missing
     dev = torch.device("cuda", local)
 
-    c = make_batch(rank, args.lengths)
+    c = make_batch(0 if args.same_seed else rank, args.lengths)
     x = c["logits"].to(dev).requires_grad_(True)
     tg, il, tl = c["targets"].to(dev), c["input_lengths"].to(dev), c["target_lengths"].to(dev)
     sum_T = int(c["input_lengths"].sum())
-    bytes_step = 4 * V_ * (2 * sum_T + B_ * T_)                 # 3-sweep algorithmic bytes
-    bytes_k3 = 4 * V_ * (sum_T + B_ * T_)                       # k3: re-read valid frames + write all of grad
+    bytes_3sweep = 4 * V_ * (2 * sum_T + B_ * T_)               # BASELINE.md section 3, primary figure
+    bytes_2sweep = 4 * V_ * (sum_T + B_ * T_)                   # what this implementation moves: read once, write once
 
     def fwd():
         if world == 1:
-            return ctc_loss_b200(x, tg, il, tl, blank=0, reduction="mean", zero_infinity=False)   # fused, chunked
+            return ctc_loss_b200(x, tg, il, tl, blank=0, reduction="mean", zero_infinity=False)
         return sharded_ctc_loss(x, tg, il, tl, blank=0, zero_infinity=False)   # 1 all-reduce of one float
 
     def step():
@@ -221,11 +400,12 @@ def main():
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     K = args.steps
-    # ---- headline: K steps of the public op (two-sweep path, gradient produced in the forward call) ----
+    W = max(args.warmup, 3)
+    # ---- headline: K steps of the public op ----
     with ClockSampler(local) as clocks:
         clocks.wait_first_sample()
         load_t0 = time.time()
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(W):
             loss = step()
         torch.cuda.synchronize()
         if world > 1:
@@ -249,25 +429,21 @@ def main():
     value = world * B_ * K / (total_ms / 1e3)
     loss_val = float(loss.item())
 
-    # ---- per-kernel timing for the roofline (live, CUDA events on the launching stream): one un-chunked
-    #      two-sweep call; the library's sweep_done event splits it into [k0_prep + fused sweep kernel]
-    #      and [lattice + sparse patch] ----
+    # ---- per-kernel timing for the roofline (live, CUDA events on the launching stream): one un-chunked call; the
+    #      library's sweep_done event splits it into [k0_prep + fused sweep kernel] and [lattice + sparse patch] ----
     from asr_chinese_e2e_b200.profiling import time_stages
     st = time_stages(x, tg, il, tl, reduction="mean", zero_infinity=False, iters=min(K, 50), warmup=3)
     sweep_ms, rest_ms = statistics.mean(st["sweep_ms"]), statistics.mean(st["rest_ms"])
 
-    n_chunks = int(os.environ.get("CTCB200_CHUNKS", "1"))
-    launches_per_step = 4 * n_chunks + 1          # per chunk: k0, k1(fused), k2, k3p; plus the (empty) rescale launch
+    launches_per_step = 5                          # k0_prep, k1_lse_gather<FUSED>, k2_lattice, k3p_patch, k4_rescale (early exit)
     peak, peak_src = peaks()
-    bytes_2sweep = bytes_k3                                     # read valid frames once + write all of grad once
     k1f_gbs = bytes_2sweep / (sweep_ms / 1e3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "k1f_traffic.json")
     if os.path.exists(tp):
-        tj = json.load(open(tp))
-        traffic = tj.get("dram_bytes_per_launch", {}).get(args.lengths)
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch", {}).get(args.lengths)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "b200",
             "config": workload_cfg(args, world), "loss": loss_val,
             "gpu_launches": launches_per_step * K,
@@ -276,38 +452,101 @@ def main():
                          "achieved": k1f_gbs, "peak": peak, "unit": "GB/s", "frac": k1f_gbs / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_2sweep,
                          "ms_per_launch": sweep_ms},
-            "roofline_step": {"algorithmic_bytes_3sweep": bytes_step, "algorithmic_bytes_2sweep": bytes_2sweep,
-                              "achieved_vs_3sweep": bytes_step / (ms_step / 1e3) / 1e9,
+            "roofline_step": {"algorithmic_bytes_3sweep": bytes_3sweep, "algorithmic_bytes_2sweep": bytes_2sweep,
+                              "achieved_vs_3sweep": bytes_3sweep / (ms_step / 1e3) / 1e9,
                               "achieved_vs_2sweep": bytes_2sweep / (ms_step / 1e3) / 1e9,
-                              "frac": bytes_step / (ms_step / 1e3) / 1e9 / peak,
+                              "frac": bytes_3sweep / (ms_step / 1e3) / 1e9 / peak,
                               "frac_2sweep": bytes_2sweep / (ms_step / 1e3) / 1e9 / peak,
                               "peak": peak, "unit": "GB/s",
                               "note": "BASELINE.md's primary figure is the 3-sweep byte count; this implementation "
-                                      "needs only 2 sweeps (+ a sparse correction), so frac can exceed the share of "
-                                      "HBM actually used (frac_2sweep)",
-                              "pipeline": f"{n_chunks} utterance chunk(s), two-sweep path, gradient produced in the "
-                                          "forward call (speculative upstream gradient 1)",
+                                      "needs only 2 sweeps (+ a sparse correction): frac_2sweep is the share of HBM "
+                                      "bandwidth the step really uses",
                               "sweep_ms": sweep_ms, "lattice_plus_patch_ms": rest_ms},
+            "lattice_stats": {"utterances": B_, "log_space": st["lattice_stats"][0],
+                              "of_which_underflowed_in_linear_domain": st["lattice_stats"][1]},
             "clocks": clock_summary}
 
-    if rank == 0 and world == 1:
-        if not args.no_e2e:
-            line["e2e"] = run_e2e(torch, c, args, dev)
-            # the training-shaped variant: the gradient's consumer is the next GPU kernel, only the loss goes back
-            line["e2e_grad_on_device"] = run_e2e(torch, c, args, dev, grad_to_host=False)
-        line["torch_cuda_baseline"] = run_torch_cuda(torch, x, tg, il, tl)
-        if not args.no_cpu:
-            cb = cpu_reference_line(args, c, steps=5, warmup=2)
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    elif world > 1:
-        e = run_e2e(torch, c, args, dev) if not args.no_e2e else None
-        if e is not None:
+    # ---- parity gate on the very tensors that were timed ----
+    if not args.no_parity:
+        nll = ctc_loss_b200(x.detach(), tg, il, tl, reduction="none", zero_infinity=False)
+        step()
+        n_par = B_ if world == 1 else 32             # N>1: a bounded per-rank sample (every rank shares the host cores)
+        par = parity_check(torch, c, nll, x.grad, n_par, inv_batch=1.0 / B_)
+        if world > 1:
+            # global loss against a host-side float64 sum over every rank's per-utterance nll
+            allnll = [torch.empty_like(nll) for _ in range(world)]
+            alltl = [torch.empty_like(tl) for _ in range(world)]
+            dist.all_gather(allnll, nll); dist.all_gather(alltl, tl)
+            host = (torch.cat(allnll).double().cpu() / torch.cat(alltl).clamp(min=1).double().cpu()).mean().item()
+            t = torch.tensor([par["nll_rel_max"], par["grad_abs_max"], 0.0 if par["pass"] else 1.0], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            par.update(nll_rel_max=float(t[0]), grad_abs_max=float(t[1]), n_utts=n_par * world,
+                       global_loss=loss_val, global_loss_host_sum=host,
+                       global_loss_rel=abs(loss_val - host) / abs(host))
+            par["pass"] = bool(t[2].item() == 0.0 and par["global_loss_rel"] <= REL_LOSS)
+        line["parity"] = par
+
+    # ---- N>1: what the collective costs (same shard, same kernels, no all-reduce) ----
+    if world > 1:
+        def local_step():
+            x.grad = None
+            loss = ctc_loss_b200(x, tg, il, tl, blank=0, reduction="mean", zero_infinity=False, inv_batch=1.0 / (world * B_))
+            loss.backward()
+            return loss
+        kk = min(K, 100)
+        dist.barrier()
+        ms_local, _ = time_steps(torch, local_step, kk, 3)
+        dist.barrier()
+        ms_coll, _ = time_steps(torch, step, kk, 3)
+        t = torch.tensor([ms_local, ms_coll], device=dev)
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tmin = t.clone(); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        line["comm"] = {"ms_per_step_without_collective_max_rank": float(tmax[0]),
+                        "ms_per_step_without_collective_min_rank": float(tmin[0]),
+                        "ms_per_step_with_collective_max_rank": float(tmax[1]),
+                        "comm_us": 1e3 * float(tmax[1] - tmax[0]),
+                        "slowest_rank_us": 1e3 * float(tmax[0] - tmin[0]),
+                        "note": "comm_us = step with the all-reduce minus the same step without it (max over ranks); "
+                                "slowest_rank_us = spread of the collective-free step across ranks (each rank draws its "
+                                "own lengths unless --same-seed)", "same_seed": bool(args.same_seed)}
+
+    if not args.no_e2e:
+        e = run_e2e(torch, c, args, dev)
+        if world > 1:
             t = torch.tensor([e["ms_per_step"]], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e["ms_per_step"] = float(t.item())
             e["value"] = world * B_ / (e["ms_per_step"] / 1e3)
             e["h2d_bytes_per_step"] *= world; e["d2h_bytes_per_step"] *= world
-            line["e2e"] = e
+        line["e2e"] = e
+        if world == 1:
+            # the training-shaped variant: the gradient's consumer is the next GPU kernel, only the loss goes back
+            line["e2e_grad_on_device"] = run_e2e(torch, c, args, dev, grad_to_host=False)
+
+    if not args.no_configs:
+        cfgs = {}
+        if world == 1:
+            from oracle.synth import make_config
+            Kc = max(10, min(K, 50))
+            cfgs["C2_full"] = sub_record(torch, "C2_full", make_batch(0, "full"), False, Kc, peak, 0,
+                                         "C2 with all lengths = T (the headline roofline point of BASELINE.md section 3)")
+            cfgs["C2_D2_sharp"] = sub_record(torch, "C2_D2", make_batch(0, args.lengths, dist="D2"), False, Kc, peak, 64,
+                                             "C2 with trained-like sharp posteriors (D2: randn + 8*onehot(alignment))")
+            x = None
+            torch.cuda.empty_cache()
+            cfgs["C4"] = sub_record(torch, "C4", make_config("C4"), True, Kc, peak, 64,
+                                    "C4: B=64, T=1500, U<=120, zero_infinity=True, 8 infeasible + 8 partial-lattice utterances")
+        x = None
+        torch.cuda.empty_cache()
+        cfgs["C5"] = c5_record(torch, dist, world, rank, dev)
+        line["configs"] = cfgs
+
+    if rank == 0 and world == 1:
+        line["torch_cuda_baseline"] = run_torch_cuda(torch, c, dev)
+        if not args.no_cpu:
+            cb = cpu_reference_line(args, c, steps=5, warmup=2)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model",
+                                                        "ms_per_step", "one_thread")}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -315,26 +554,18 @@ def main():
         dist.destroy_process_group()
 
 
-def run_torch_cuda(torch, x, tg, il, tl):
+def run_torch_cuda(torch, c, dev):
     """Secondary GPU baseline: torch's own CUDA log_softmax + ctc_loss + backward on the same
     B200 and inputs -- what the reference as written would execute once a CTC call were added."""
     import torch.nn.functional as F
+    x = c["logits"].to(dev).requires_grad_(True)
+    tg, il, tl = c["targets"].to(dev), c["input_lengths"].to(dev), c["target_lengths"].to(dev)
 
     def step():
         x.grad = None
         F.ctc_loss(F.log_softmax(x, -1).transpose(0, 1), tg, il, tl, blank=0, reduction="mean",
                    zero_infinity=False).backward()
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    x.grad = None
-    ms = e0.elapsed_time(e1) / 10
+    ms, _ = time_steps(torch, step, 10, 3)
     return {"value": B_ / (ms / 1e3), "unit": UNIT, "ms_per_step": ms,
             "what": f"torch {torch.__version__} CUDA F.log_softmax + F.ctc_loss(mean) + backward, same inputs, 10 steps"}
 
@@ -357,12 +588,15 @@ def run_e2e(torch, c, args, dev, grad_to_host=True):
     torch.cuda.synchronize()
     ms = 1e3 * (time.perf_counter() - t0) / k
     loss = float((h_n / h_tl.clamp(min=1).float()).mean())
-    return {"value": B_ / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
-            "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": ms, "steps": k, "loss": loss,
+    h2d, d2h, launches = pipe.h2d_bytes, pipe.d2h_bytes, pipe.launches_per_step
+    del pipe
+    torch.cuda.empty_cache()
+    return {"value": B_ / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "ms_per_step": ms, "steps": k, "loss": loss,
             "api": "asr_chinese_e2e_b200.host_pipeline.HostCTCPipeline (pinned host logits in; "
                    + ("grad[B,T,V] + " if grad_to_host else "gradient left on the device, ")
                    + "nll[B] back to pinned host; 3-stream chunked pipeline, chunk=32 utterances)",
-            "gpu_launches_per_step": pipe.launches_per_step}
+            "gpu_launches_per_step": launches}
 
 
 if __name__ == "__main__":

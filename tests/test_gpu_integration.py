@@ -104,6 +104,7 @@ def test_sharded_wrapper_single_rank_and_debug_status():
     assert L.ctcb200_read_status(ws.data_ptr(), ctypes.byref(status), st) == 0
     assert status.value & 1 and status.value & 4
     assert torch.isfinite(nll[2:]).all()
+    assert torch.isnan(nll[:2]).all()            # the two invalid utterances are poisoned, not silently clamped
 
 
 def test_no_out_of_bounds_writes_guard_zones():
