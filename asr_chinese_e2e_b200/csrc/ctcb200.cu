@@ -45,7 +45,9 @@ Opt g_opt[OPT_COUNT] = {
     {"k1f_direct", "CTCB200_K1F_DIRECT", 0}, {"k1f_carveout", "CTCB200_K1F_CARVEOUT", 40},
     {"zero_in_lattice", "CTCB200_ZERO_IN_LATTICE", 0}, {"zero_cps", "CTCB200_ZERO_CPS", 2},
     {"skip_lattice", "CTCB200_DEBUG_SKIP_LATTICE", 0},  // profiling aid: time the sweep alone
-    {"label_keep_l2", "CTCB200_LABEL_KEEP_L2", 1},      // fused sweep: evict_last for gradient chunks the patch revisits
+    // fused sweep: evict_last for the gradient chunks the sparse patch revisits.  Measured on B200 (round 2): the patch
+    // still misses L2 (104 MB of DRAM reads either way) and the sweep gets 4 us slower -> off
+    {"label_keep_l2", "CTCB200_LABEL_KEEP_L2", 0},
 };
 const bool g_opt_loaded = [] {
     for (Opt &o : g_opt) {

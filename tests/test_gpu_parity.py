@@ -285,7 +285,9 @@ def test_fused_pipeline_equals_unfused_and_rescales():
     ga = x.grad.clone()
     x.grad = None
     nll.backward(go)
-    assert torch.equal(ga, x.grad)
+    # a second backward of a retained graph recomputes the gradient out of place with the three-sweep kernel (the
+    # buffer handed out by the first backward is never written again): same values up to fp32 rounding
+    assert (ga - x.grad).abs().max().item() <= 1e-5 * ga.abs().max().item()
     _, rg = ref_ctc(c["logits"], c["targets"], c["input_lengths"], c["target_lengths"], reduction="none",
                     zero_infinity=True, grad_output=go.cpu())
     assert_grad_close(ga.cpu(), rg, "none fused", tol=1e-3)
