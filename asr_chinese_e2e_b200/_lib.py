@@ -13,12 +13,12 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(_HERE, "libctcb200.so")
-SOURCES = ["ctcb200.cu"]
+SOURCES = ["ctcb200.cu", "head.cu"]
 HEADERS = ["ptx.cuh", "layout.h", "stream_kernels.cuh", "lattice_kernel.cuh", "lattice_lin.cuh", "ce_kernel.cuh", "decode_kernel.cuh",
-           os.path.join("..", "..", "include", "ctcb200.h")]
+           "head_kernels.cuh", "internal.h", os.path.join("..", "..", "include", "ctcb200.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "128"]
+              "-Xcompiler", "-fPIC", "-diag-suppress", "128"]
 
 
 def needs_build() -> bool:
@@ -33,9 +33,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return SO_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", SO_PATH] + [os.path.join(_CSRC, s) for s in SOURCES]
-    subprocess.check_call(cmd)
+    bdir = os.path.join(_HERE, "build")
+    os.makedirs(bdir, exist_ok=True)
+    # one object per translation unit, compiled in parallel; then one link into the in-tree shared library
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(bdir, os.path.splitext(src)[0] + ".o")
+        objs.append(obj)
+        newest = max(os.path.getmtime(os.path.join(_CSRC, f)) for f in [src] + HEADERS)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > newest:
+            continue
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(_CSRC, src)]
+        procs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO_PATH] + objs)
     return SO_PATH
 
 
@@ -64,6 +77,10 @@ SIGNATURES = {
     "ctcb200_edit_distance": (_i, [_p, _i64, _p, _i64, _i, _i, _i, _i, _p, _p, _p]),
     "ctcb200_ce_workspace_bytes": (_i, [_i64, ctypes.POINTER(_sz)]),
     "ctcb200_ce_loss_grad": (_i, [_p, _p, _i64, _i, _i, _f, _f, _p, _p, _p, _sz, _p]),
+    "ctcb200_head_workspace_bytes": (_i, [_i, _i, _i, _i, _i, _i, ctypes.POINTER(_sz)]),
+    "ctcb200_head_loss": (_i, [_p, _p, _p, _p, _i64, _i64, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
+    "ctcb200_head_loss_grad": (_i, [_p, _p, _p, _p, _i64, _i64, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p,
+                                    _p, _i64, _p, _sz, _p]),
     "ctcb200_read_status": (_i, [_p, ctypes.POINTER(_i), _p]),
     "ctcb200_read_lattice_stats": (_i, [_p, ctypes.POINTER(_i), _p]),
 }
@@ -94,6 +111,12 @@ def strerror(code: int) -> str:
 def check(code: int, what: str) -> None:
     if code != 0:
         raise CtcB200Error(f"{what} failed: [{code}] {strerror(code)}")
+
+
+def head_workspace_bytes(B: int, T: int, V: int, K: int, Umax: int, precision: int) -> int:
+    out = _sz(0)
+    check(lib().ctcb200_head_workspace_bytes(B, T, V, K, Umax, precision, ctypes.byref(out)), "ctcb200_head_workspace_bytes")
+    return int(out.value)
 
 
 def set_option(name: str, value: int) -> None:

@@ -9,6 +9,7 @@
 
 #include "ce_kernel.cuh"
 #include "decode_kernel.cuh"
+#include "internal.h"
 #include "lattice_lin.cuh"
 #include "layout.h"
 #include "stream_kernels.cuh"
@@ -362,6 +363,61 @@ cudaError_t launch_kce(const StreamCfg &c, cudaStream_t s, bool want_grad, const
 }
 
 }  // namespace
+
+namespace ctcb200 {
+
+int internal_sm_count(int *sms) {
+    DevInfo d;
+    const int rc = device_info(&d);
+    if (!rc) *sms = d.sms;
+    return rc;
+}
+
+float internal_lin_thr(const Geom &g, int flags) {
+    const int lattice_mode = opt(OPT_LATTICE_LOG) || (flags & CTCB200_FLAG_LATTICE_LOG);
+    const int thr_env = opt(OPT_LIN_THR);
+    return lattice_mode ? 1.f : -(float)(thr_env > 0 ? thr_env : 900 / (lin_tile_frames(g.NS) + g.NS / 2));
+}
+
+float internal_occ_skip() {
+    const int skip_bits = opt(OPT_OCC_SKIP_BITS);
+    return skip_bits > 0 ? ldexpf(1.f, -skip_bits) : 0.f;
+}
+
+int internal_prep(const int64_t *in_len, const int64_t *tgt_len, int64_t targets_stride, int B, int T, int Umax,
+                  void *workspace, const Workspace &w, cudaStream_t s) {
+    unsigned char *ws = (unsigned char *)workspace;
+    prefer_max_carveout(k0_prep);
+    k0_prep<<<1, 1024, 0, s>>>(in_len, tgt_len, targets_stride, B, T, Umax, (int *)(ws + w.hdr), (int *)(ws + w.Tb),
+                               (int *)(ws + w.Ub), (int *)(ws + w.flags), (int64_t *)(ws + w.toff),
+                               (int *)(ws + w.rowstart), (int *)(ws + w.slow), (int *)(ws + w.bad));
+    return (int)cudaGetLastError();
+}
+
+int internal_lattice(bool want_grad, const int64_t *targets, int64_t tnumel, int B, int T, int V, int zero_infinity,
+                     float *nll, float *loss_sums, float mean_scale, void *workspace, const Workspace &w, const Geom &g,
+                     cudaStream_t s) {
+    unsigned char *ws = (unsigned char *)workspace;
+    int *hdr = (int *)(ws + w.hdr);
+    cudaError_t e;
+#define K2_ARGS s, targets, tnumel, (int *)(ws + w.Tb), (int *)(ws + w.Ub), (int64_t *)(ws + w.toff),                    \
+                (int *)(ws + w.flags), (float *)(ws + w.lp_lab), (float *)(ws + w.gam), (float *)(ws + w.ab), nll,         \
+                loss_sums, (unsigned *)(hdr + 1), B, T, zero_infinity & 1, (float *)nullptr, (int *)(ws + w.rowstart), V, \
+                0, (double *)(ws + w.tile_off), mean_scale, (int *)(ws + w.slow), w.ab_utt, false, (int *)(ws + w.bad)
+    if (want_grad) {
+        if (g.NS == 4) e = launch_k2<4, true>(K2_ARGS);
+        else if (g.NS == 8) e = launch_k2<8, true>(K2_ARGS);
+        else e = launch_k2<16, true>(K2_ARGS);
+    } else {
+        if (g.NS == 4) e = launch_k2<4, false>(K2_ARGS);
+        else if (g.NS == 8) e = launch_k2<8, false>(K2_ARGS);
+        else e = launch_k2<16, false>(K2_ARGS);
+    }
+#undef K2_ARGS
+    return (int)e;
+}
+
+}  // namespace ctcb200
 
 extern "C" {
 

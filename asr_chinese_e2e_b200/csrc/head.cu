@@ -1,0 +1,199 @@
+// C-ABI of the fused CTC head (include/ctcb200.h, ctcb200_head_*): TMA tensor maps, workspace carve-up and the
+// launch sequence  prep -> [operand split] -> k_head<pass 1> -> lattice -> k_head<pass 2>.
+#include "../../include/ctcb200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "head_kernels.cuh"
+#include "internal.h"
+#include "layout.h"
+
+using namespace ctcb200;
+
+namespace {
+
+constexpr size_t kSmemBudget = 226 * 1024;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: the library does not link libcuda, so it still
+// loads (and its argument validation still runs) on a machine without a driver
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// fp32 matrix [rows, K] row-major (K contiguous) -> boxes of box_rows x 32 floats (128 B), SWIZZLE_128B; rows past the
+// end read as zeros
+int make_map(CUtensorMap *m, const float *base, int64_t rows, int K, int box_rows) {
+    EncodeTiledFn f = encode_fn();
+    if (!f) return CTCB200_ERR_NO_DEVICE;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)HK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : CTCB200_ERR_SHAPE;
+}
+
+struct HeadWs {
+    Workspace ctc;
+    size_t enc_hi, enc_lo, w_hi, w_lo, total;
+};
+
+HeadWs head_layout(int B, int T, int V, int K, const Geom &g, int precision) {
+    HeadWs h;
+    h.ctc = workspace_layout(B, T, g);
+    size_t o = h.ctc.total;
+    const size_t ne = align_up((size_t)(B > 0 ? B : 1) * T * K * 4), nw = align_up((size_t)V * K * 4);
+    h.enc_hi = h.enc_lo = h.w_hi = h.w_lo = 0;
+    if (precision == CTCB200_HEAD_3XTF32) {
+        h.enc_hi = o; o += ne;
+        h.enc_lo = o; o += ne;
+        h.w_hi = o;   o += nw;
+        h.w_lo = o;   o += nw;
+    }
+    h.total = o;
+    return h;
+}
+
+int check_head(const float *enc, const float *weight, const void *targets, const void *in_len, const void *tgt_len,
+               int B, int T, int V, int K, int Umax, int blank, int precision, const void *ws, size_t ws_bytes, Geom *g,
+               HeadWs *h) {
+    if (B < 0 || T < 1 || V < 2 || K < HK || (K % HK) != 0 || (long long)B * T > 0x7fffff00LL) return CTCB200_ERR_SHAPE;
+    if (blank < 0 || blank >= V) return CTCB200_ERR_BLANK;
+    if (!geom_for(Umax, g)) return CTCB200_ERR_UMAX;
+    if (precision != CTCB200_HEAD_3XTF32 && precision != CTCB200_HEAD_TF32) return CTCB200_ERR_OPTION;
+    if (!enc || !weight || !targets || !in_len || !tgt_len || !ws) return CTCB200_ERR_NULL;
+    if (((uintptr_t)enc & 15) || ((uintptr_t)weight & 15) || ((uintptr_t)ws & 255)) return CTCB200_ERR_ALIGN;
+    *h = head_layout(B, T, V, K, *g, precision);
+    if (ws_bytes < h->total) return CTCB200_ERR_WORKSPACE;
+    return 0;
+}
+
+template <int NPASS, bool GRADPASS>
+int launch_head(int sms, cudaStream_t s, const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &b_hi,
+                const CUtensorMap &b_lo, const HeadArgs &args) {
+    constexpr size_t smem = HeadCfg<NPASS>::SMEM;
+    static_assert(smem <= kSmemBudget, "shared memory budget");
+    cudaError_t e = cudaFuncSetAttribute(k_head<NPASS, GRADPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int M = args.B * args.T, n_tiles = (M + HM - 1) / HM;
+    const int grid = n_tiles < sms ? n_tiles : sms;
+    k_head<NPASS, GRADPASS><<<grid, H_THREADS, smem, s>>>(a_hi, a_lo, b_hi, b_lo, args);
+    return (int)cudaGetLastError();
+}
+
+int head_impl(bool want_grad, const float *enc, const float *weight, const float *bias, const int64_t *targets,
+              int64_t targets_stride, int64_t targets_numel, const int64_t *in_len, const int64_t *tgt_len, int B, int T,
+              int V, int K, int Umax, int blank, int flags, int precision, int reduction, float inv_batch, float *nll,
+              float *loss_sums, float *dlogits, int64_t dlogits_pitch, void *workspace, size_t workspace_bytes,
+              ctcb200_stream_t stream) {
+    Geom g;
+    HeadWs h;
+    int rc = check_head(enc, weight, targets, in_len, tgt_len, B, T, V, K, Umax, blank, precision, workspace,
+                        workspace_bytes, &g, &h);
+    if (rc) return rc;
+    if (!nll) return CTCB200_ERR_NULL;
+    if (targets_stride < 0 || targets_numel < 0) return CTCB200_ERR_SHAPE;
+    if (flags & CTCB200_FLAG_DECODE) return CTCB200_ERR_OPTION;          // no per-frame argmax on this path (yet)
+    if (want_grad) {
+        if (!dlogits) return CTCB200_ERR_NULL;
+        if ((uintptr_t)dlogits & 15) return CTCB200_ERR_ALIGN;
+        if (dlogits_pitch < V || (dlogits_pitch & 3) || dlogits_pitch >= (int64_t)V + 32) return CTCB200_ERR_SHAPE;
+        if (reduction < 0 || reduction > 2) return CTCB200_ERR_REDUCTION;
+    }
+    if (B == 0) return CTCB200_OK;
+    int sms = 0;
+    if ((rc = internal_sm_count(&sms))) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned char *ws = (unsigned char *)workspace;
+    const int64_t tnumel = targets_stride ? (int64_t)B * targets_stride : targets_numel;
+    const int zero_inf = flags & 1;
+
+    if ((rc = internal_prep(in_len, tgt_len, targets_stride, B, T, Umax, workspace, h.ctc, s))) return rc;
+
+    const float *a_hi = enc, *a_lo = enc, *b_hi = weight, *b_lo = weight;
+    if (precision == CTCB200_HEAD_3XTF32) {
+        float *eh = (float *)(ws + h.enc_hi), *el = (float *)(ws + h.enc_lo), *wh = (float *)(ws + h.w_hi),
+              *wl = (float *)(ws + h.w_lo);
+        const size_t ne4 = (size_t)B * T * K / 4, nw4 = (size_t)V * K / 4;       // K % 32 == 0
+        k_split_tf32<<<sms * 8, 256, 0, s>>>(enc, eh, el, ne4);
+        k_split_tf32<<<sms * 2, 256, 0, s>>>(weight, wh, wl, nw4);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+        a_hi = eh; a_lo = el; b_hi = wh; b_lo = wl;
+    }
+    CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+    if ((rc = make_map(&mA_hi, a_hi, (int64_t)B * T, K, HM)) || (rc = make_map(&mA_lo, a_lo, (int64_t)B * T, K, HM)) ||
+        (rc = make_map(&mB_hi, b_hi, V, K, HN)) || (rc = make_map(&mB_lo, b_lo, V, K, HN)))
+        return rc;
+
+    HeadArgs a;
+    a.bias = bias; a.targets = targets; a.tnumel = tnumel;
+    a.Tb = (const int *)(ws + h.ctc.Tb); a.Ub = (const int *)(ws + h.ctc.Ub); a.toff = (const int64_t *)(ws + h.ctc.toff);
+    a.flags = (const int *)(ws + h.ctc.flags); a.slow = (int *)(ws + h.ctc.slow); a.bad = (int *)(ws + h.ctc.bad);
+    a.hdr = (int *)(ws + h.ctc.hdr);
+    a.lp_lab = (float *)(ws + h.ctc.lp_lab); a.gam = (const float *)(ws + h.ctc.gam);
+    a.dlogits = dlogits; a.pitch = dlogits_pitch;
+    a.B = B; a.T = T; a.V = V; a.K = K; a.Lp = g.Lp; a.blank = blank; a.zero_inf = zero_inf; a.reduction = reduction;
+    a.inv_batch = inv_batch; a.lin_thr = internal_lin_thr(g, flags); a.occ_skip = internal_occ_skip();
+
+    rc = precision == CTCB200_HEAD_3XTF32 ? launch_head<3, false>(sms, s, mA_hi, mA_lo, mB_hi, mB_lo, a)
+                                          : launch_head<1, false>(sms, s, mA_hi, mA_lo, mB_hi, mB_lo, a);
+    if (rc) return rc;
+    const float mean_scale = want_grad ? inv_batch : 1.f / (float)B;
+    if ((rc = internal_lattice(want_grad, targets, tnumel, B, T, V, zero_inf, nll, loss_sums, mean_scale, workspace, h.ctc,
+                               g, s)))
+        return rc;
+    if (!want_grad) return CTCB200_OK;
+    return precision == CTCB200_HEAD_3XTF32 ? launch_head<3, true>(sms, s, mA_hi, mA_lo, mB_hi, mB_lo, a)
+                                            : launch_head<1, true>(sms, s, mA_hi, mA_lo, mB_hi, mB_lo, a);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ctcb200_head_workspace_bytes(int B, int T, int V, int K, int Umax, int precision, size_t *out_bytes) {
+    if (!out_bytes) return CTCB200_ERR_NULL;
+    if (B < 0 || T < 1 || V < 2 || K < HK || (K % HK) != 0) return CTCB200_ERR_SHAPE;
+    if (precision != CTCB200_HEAD_3XTF32 && precision != CTCB200_HEAD_TF32) return CTCB200_ERR_OPTION;
+    Geom g;
+    if (!geom_for(Umax, &g)) return CTCB200_ERR_UMAX;
+    *out_bytes = head_layout(B, T, V, K, g, precision).total;
+    return CTCB200_OK;
+}
+
+int ctcb200_head_loss(const float *enc, const float *weight, const float *bias, const int64_t *targets,
+                      int64_t targets_stride, int64_t targets_numel, const int64_t *in_len, const int64_t *tgt_len, int B,
+                      int T, int V, int K, int Umax, int blank, int flags, int precision, float *nll, float *loss_sums,
+                      void *workspace, size_t workspace_bytes, ctcb200_stream_t stream) {
+    return head_impl(false, enc, weight, bias, targets, targets_stride, targets_numel, in_len, tgt_len, B, T, V, K, Umax,
+                     blank, flags, precision, 0, 0.f, nll, loss_sums, nullptr, 0, workspace, workspace_bytes, stream);
+}
+
+int ctcb200_head_loss_grad(const float *enc, const float *weight, const float *bias, const int64_t *targets,
+                           int64_t targets_stride, int64_t targets_numel, const int64_t *in_len, const int64_t *tgt_len,
+                           int B, int T, int V, int K, int Umax, int blank, int flags, int precision, int reduction,
+                           float inv_batch, float *nll, float *loss_sums, float *dlogits, int64_t dlogits_pitch,
+                           void *workspace, size_t workspace_bytes, ctcb200_stream_t stream) {
+    return head_impl(true, enc, weight, bias, targets, targets_stride, targets_numel, in_len, tgt_len, B, T, V, K, Umax,
+                     blank, flags, precision, reduction, inv_batch, nll, loss_sums, dlogits, dlogits_pitch, workspace,
+                     workspace_bytes, stream);
+}
+
+}  // extern "C"

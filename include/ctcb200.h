@@ -201,6 +201,39 @@ int ctcb200_ce_loss_grad(const float *pred, const int64_t *gold, int64_t rows, i
                          float smoothing, float weight, float *loss_out, float *grad, void *workspace,
                          size_t workspace_bytes, ctcb200_stream_t stream);
 
+/* ---- f1: the CTC head fused with the loss -------------------------------------------------
+ * logits = enc[B*T, K] x weight[V, K]^T + bias[V]  (the nn.Linear(d_model, vocab) the joint model attaches to the
+ * encoder output, Predictor/Models/transformer_official.py:76) is computed tile by tile on the tensor cores
+ * (tcgen05.mma kind::tf32, fp32 accumulators in TMEM, operands staged by TMA) and consumed in the epilogue: the
+ * [B,T,V] logits tensor is never written to or read from HBM.
+ *   ctcb200_head_loss       forward / evaluation: per-row log-sum-exp + label gather in the GEMM epilogue, then the
+ *                           alpha/beta lattice.  Same outputs as ctcb200_loss_only on F.linear(enc, weight, bias).
+ *   ctcb200_head_loss_grad  training: the same forward, the lattice with occupancies, then a second GEMM pass that
+ *                           recomputes each logits tile and writes d loss / d logits = g_b * (softmax - occupancy)
+ *                           (zeros for padded frames) to dlogits[B*T, dlogits_pitch] (pitch: multiple of 4, V <=
+ *                           pitch < V + 32, so rows stay 16-byte aligned; columns >= V are written as zeros).  The
+ *                           caller forms d weight = dlogits^T x enc, d enc = dlogits x weight, d bias = column sums
+ *                           with plain library GEMMs.  g_b as in ctcb200_loss_grad (upstream gradient 1).
+ * precision: CTCB200_HEAD_3XTF32 -- operands split as hi + lo (tf32 each), hi*hi + hi*lo + lo*hi accumulated in fp32:
+ *            fp32-GEMM grade (meets the 1e-5 relative bar on the per-utterance loss); CTCB200_HEAD_TF32 -- one pass,
+ *            10-bit mantissa operands (like torch.backends.cuda.matmul.allow_tf32), 3x fewer tensor-core passes.
+ * K (d_model) must be a multiple of 32; enc and weight 16-byte aligned, row-major, contiguous.  bias may be NULL.
+ * The workspace (ctcb200_head_workspace_bytes) holds the CTC workspace plus, for 3XTF32, the split operands. */
+enum ctcb200_head_precision { CTCB200_HEAD_3XTF32 = 0, CTCB200_HEAD_TF32 = 1 };
+
+int ctcb200_head_workspace_bytes(int B, int T, int V, int K, int Umax, int precision, size_t *out_bytes);
+
+int ctcb200_head_loss(const float *enc, const float *weight, const float *bias, const int64_t *targets,
+                      int64_t targets_stride, int64_t targets_numel, const int64_t *in_len, const int64_t *tgt_len, int B,
+                      int T, int V, int K, int Umax, int blank, int flags, int precision, float *nll, float *loss_sums,
+                      void *workspace, size_t workspace_bytes, ctcb200_stream_t stream);
+
+int ctcb200_head_loss_grad(const float *enc, const float *weight, const float *bias, const int64_t *targets,
+                           int64_t targets_stride, int64_t targets_numel, const int64_t *in_len, const int64_t *tgt_len,
+                           int B, int T, int V, int K, int Umax, int blank, int flags, int precision, int reduction,
+                           float inv_batch, float *nll, float *loss_sums, float *dlogits, int64_t dlogits_pitch,
+                           void *workspace, size_t workspace_bytes, ctcb200_stream_t stream);
+
 /* Debug: copies the device status word to *host_status (synchronises `stream`). */
 int ctcb200_read_status(const void *workspace, int *host_status, ctcb200_stream_t stream);
 
