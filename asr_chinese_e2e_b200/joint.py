@@ -25,6 +25,7 @@ import torch.nn.functional as F
 
 from .ce import attention_ce_b200
 from .ctc import ctc_loss_b200
+from .head import ctc_head_loss_b200
 from .metrics import seq_cer_b200
 
 IGNORE_ID = 0   # PAD id of the reference vocab == CTC blank (Predictor/Utils/loss.py:5, vocab.py:10)
@@ -131,9 +132,12 @@ class JointCTCAttention:
 
     ctc_weight: float = 0.3
     ctc_zero_infinity: bool = True
+    ctc_fused_head: bool = False
+    ctc_head_precision: str = "3xtf32"
 
     def init_ctc(self, d_model: int, vocab_size: int, ctc_weight: float = 0.3, ctc_zero_infinity: bool = True,
-                 smoothing: float = 0.0, ctc_cer_on_device: bool = True):
+                 smoothing: float = 0.0, ctc_cer_on_device: bool = True, fused_head: bool = False,
+                 head_precision: str = "3xtf32"):
         self.ctc_head = torch.nn.Linear(d_model, vocab_size)
         self.ctc_weight = float(ctc_weight)
         self.ctc_zero_infinity = bool(ctc_zero_infinity)
@@ -141,15 +145,21 @@ class JointCTCAttention:
         # on CUDA batches: adds a `ctc_cer` metric (greedy CTC decode + edit distance of the same forward pass,
         # device-side, no sync); the attention-branch `cer` is computed on the device either way
         self.ctc_cer_on_device = bool(ctc_cer_on_device)
+        # f1: compute ctc_head and the CTC loss in one tcgen05 kernel pair (head.py); the [B,T,V] CTC logits then never
+        # exist, forward() hands the encoder output on instead (and there is no `ctc_cer` by-product)
+        self.ctc_fused_head = bool(fused_head)
+        self.ctc_head_precision = head_precision
 
     # -- forward: encoder tap + CTC head, then the decoder exactly as the reference calls it --------
     def forward(self, input):
         enc, *_ = self.encoder(input.wave, input.wave_len)
         pred, gold, *_ = self.decoder(input.tgt_for_input, enc, input.tgt_len)
+        if self.ctc_fused_head and enc.is_cuda and enc.shape[-1] % 32 == 0:
+            return Pack(pred=pred, gold=gold, ctc_enc=enc)
         return Pack(pred=pred, gold=gold, ctc_logits=self.ctc_head(enc))
 
     def joint_loss(self, output, input):
-        if output.ctc_logits is None:          # Pack returns None for a missing key (pack.py:7-8)
+        if output.ctc_logits is None and output.ctc_enc is None:   # Pack returns None for a missing key (pack.py:7-8)
             raise KeyError("output Pack has no 'ctc_logits': forward() must add the CTC head output")
         w = self.ctc_weight
         eps = getattr(self, "att_smoothing", 0.0)
@@ -158,7 +168,16 @@ class JointCTCAttention:
             att = attention_ce_b200(output.pred.float(), output.gold, eps, weight=1.0 - w) / (1.0 - w)
         else:
             att = attention_ce(output.pred, output.gold, eps)
-        B = output.ctc_logits.shape[0]
+        B = (output.ctc_logits if output.ctc_logits is not None else output.ctc_enc).shape[0]
+        if output.ctc_logits is None:          # fused head: logits = ctc_head(enc) never materialised
+            self._last_decode = None
+            wctc = ctc_head_loss_b200(output.ctc_enc.float(), self.ctc_head.weight, self.ctc_head.bias,
+                                      input.tgt_for_input, input.wave_len, input.tgt_len, blank=IGNORE_ID,
+                                      reduction="mean", zero_infinity=self.ctc_zero_infinity,
+                                      inv_batch=(w if w > 0 else 1.0) / max(B, 1), precision=self.ctc_head_precision)
+            if w > 0:
+                return wctc + (1.0 - w) * att, wctc / w, att
+            return att + 0.0 * wctc, wctc, att
         # ctc_weight is folded into the op's normaliser (inv_batch = w/B): the op returns w*ctc and its
         # speculative gradient is already the final one, so backward() costs one empty launch instead of a
         # rescaling sweep over [B,T,V]
