@@ -13,6 +13,7 @@
 #include "lattice_lin.cuh"
 #include "layout.h"
 #include "stream_kernels.cuh"
+#include "sweep_warp.cuh"
 
 using namespace ctcb200;
 
@@ -27,7 +28,8 @@ constexpr size_t kSmemBudget = 226 * 1024;   // leave 1 KB of the 227 KB opt-in 
 enum OptId {
     OPT_PDL, OPT_LATTICE_LOG, OPT_LIN_THR, OPT_K1F_NT, OPT_K1F_NST, OPT_K1F_CPS, OPT_K1_NT, OPT_K1_NST, OPT_K1_CPS,
     OPT_K3_NT, OPT_K3_NST, OPT_K3_CPS, OPT_CE_NST, OPT_CE_CPS, OPT_K3P_CPS, OPT_OCC_SKIP_BITS, OPT_K1F_DIRECT,
-    OPT_K1F_CARVEOUT, OPT_ZERO_IN_LATTICE, OPT_ZERO_CPS, OPT_SKIP_LATTICE, OPT_LABEL_KEEP_L2, OPT_COUNT
+    OPT_K1F_CARVEOUT, OPT_ZERO_IN_LATTICE, OPT_ZERO_CPS, OPT_SKIP_LATTICE, OPT_LABEL_KEEP_L2, OPT_SWEEP_WARP,
+    OPT_K1W_NW, OPT_K1W_NSLOT, OPT_COUNT
 };
 struct Opt { const char *name, *env; int value; };
 Opt g_opt[OPT_COUNT] = {
@@ -49,6 +51,11 @@ Opt g_opt[OPT_COUNT] = {
     // fused sweep: evict_last for the gradient chunks the sparse patch revisits.  Measured on B200 (round 2): the patch
     // still misses L2 (104 MB of DRAM reads either way) and the sweep gets 4 us slower -> off
     {"label_keep_l2", "CTCB200_LABEL_KEEP_L2", 0},
+    // the sweep of round 2 (sweep_warp.cuh: aligned frame groups, one warp per frame, no block barriers); 0 = the
+    // round-1 kernel k1_lse_gather for every shape (it remains the fallback for odd V / odd T)
+    {"sweep_warp", "CTCB200_SWEEP_WARP", 1},
+    {"k1w_nw", "CTCB200_K1W_NW", 0},                    // consumer warps per CTA (0 = auto)
+    {"k1w_nslot", "CTCB200_K1W_NSLOT", 0},              // ring slots (0 = as many as fit)
 };
 const bool g_opt_loaded = [] {
     for (Opt &o : g_opt) {
@@ -218,17 +225,51 @@ cudaError_t launch_k2(cudaStream_t s, const int64_t *targets, int64_t tnumel, co
                       zero_grad, rowstart, V, tile_off, mean_scale, slow, ab_utt, bad);
 }
 
-struct FusedGrad {          // non-null grad => 2-sweep mode: the sweep writes g*softmax, k3p adds -g*occupancy
-    float *grad; int reduction; float inv_batch;
-    int stages;             // bit 0: prep + sweep, bit 1: lattice, bit 2: sparse patch (7 = the whole call)
-};
-
 // Every kernel of the path asks for the maximum shared-memory carveout: a launch whose carveout differs
 // from the previous kernel's makes the SMs drain and reconfigure (several microseconds per launch).
 template <typename K>
 void prefer_max_carveout(K kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
+
+// Frames per aligned group of the warp sweep: the smallest P with P * V * 4 a multiple of 16; 0 = not applicable
+// (odd V would need groups of four frames; T must be a multiple of P so that no group spans two utterances).
+int group_frames(int V, int T) {
+    const int P = (V % 4 == 0) ? 1 : ((V % 2 == 0) ? 2 : 0);
+    if (P == 0 || T % P != 0) return 0;
+    return P;
+}
+
+// k1w_sweep launch; returns false (and launches nothing) when the shape does not fit
+template <bool FUSED>
+bool try_launch_k1w(cudaStream_t s, const DevInfo &dev, K1wArgs a, cudaError_t *err) {
+    const int P = a.P;
+    if (P <= 0 || !opt(OPT_SWEEP_WARP)) return false;
+    const uint32_t slot = (uint32_t)align_up((size_t)P * a.V * 4, 128);
+    int nw = opt_or(OPT_K1W_NW, 4);
+    if (nw < 2) nw = 2;
+    if (nw == 7) nw = 6;
+    if (nw > KW_MAX_CONSUMERS) nw = KW_MAX_CONSUMERS;
+    const size_t fixed = 16 * 16 + (size_t)KW_MAX_CONSUMERS * a.Lp * 4 + 128;
+    int nslot = (int)((kSmemBudget - fixed) / slot);
+    if (nslot > 16) nslot = 16;
+    const int want = opt(OPT_K1W_NSLOT);
+    if (want > 0 && want < nslot) nslot = want;
+    if (nslot < nw + 1) nw = nslot - 1;
+    if (nw < 2) return false;                            // a group does not fit the ring often enough: old kernel
+    a.nslot = nslot; a.slot_bytes = slot; a.nw = nw;
+    const size_t smem = (size_t)nslot * slot + 16 * nslot + (size_t)nw * a.Lp * 4 + 64;
+    *err = cudaFuncSetAttribute(k1w_sweep<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (*err != cudaSuccess) return true;
+    prefer_max_carveout(k1w_sweep<FUSED>);
+    *err = launch_pdl(0, k1w_sweep<FUSED>, dim3(dev.sms), dim3(32 * (nw + 1)), smem, s, a);
+    return true;
+}
+
+struct FusedGrad {          // non-null grad => 2-sweep mode: the sweep writes g*softmax, k3p adds -g*occupancy
+    float *grad; int reduction; float inv_batch;
+    int stages;             // bit 0: prep + sweep, bit 1: lattice, bit 2: sparse patch (7 = the whole call)
+};
 
 int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const int64_t *targets, int64_t targets_stride,
                  int64_t targets_numel, const int64_t *in_len, const int64_t *tgt_len, int B, int T, int V,
@@ -272,7 +313,10 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     cudaError_t e = cudaSuccess;
     if (stages & 1) {
     prefer_max_carveout(k0_prep);
-    k0_prep<<<1, 1024, 0, s>>>(in_len, tgt_len, targets_stride, B, T, Umax, hdr, Tb, Ub, flags, toff, rowstart, slow, bad);
+    const int P = group_frames(V, T);
+    int *gstart = (int *)(ws + w.gstart);
+    k0_prep<<<1, 1024, 0, s>>>(in_len, tgt_len, targets_stride, B, T, Umax, hdr, Tb, Ub, flags, toff, rowstart, slow, bad,
+                               P > 0 ? P : 1, gstart);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
 
@@ -290,7 +334,11 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
         const K1Args a = {logits, targets, tnumel, Tb, Ub, toff, rowstart, lp_lab, hdr, B, T, V, g.Lp, blank,
                           fused ? fg->grad : nullptr, fused ? fg->reduction : 0, fused ? fg->inv_batch : 0.f,
                           want_argmax ? (int *)(ws + w.best) : nullptr, zero_in_lattice ? 0 : 1, slow, lin_thr, bad};
-        if (fused && nt1 == 128 && opt(OPT_K1F_DIRECT)) {
+        K1wArgs wa = {logits, targets, tnumel, Tb, Ub, toff, rowstart, gstart, lp_lab, hdr, B, T, V, g.Lp, blank, P,
+                      0, 0u, 0, a.grad, a.reduction, a.inv_batch, a.best, a.zero_pad_here, slow, lin_thr, bad};
+        if (fused ? try_launch_k1w<true>(s, dev, wa, &e) : try_launch_k1w<false>(s, dev, wa, &e)) {
+            // launched (or failed to launch: e) the warp sweep
+        } else if (fused && nt1 == 128 && opt(OPT_K1F_DIRECT)) {
             // direct-load sweep (experiment): no ring -> shared memory = reduction scratch, class table, one row
             c.nst = 0; c.slot_bytes = 0;
             c.smem = (96 + (size_t)g.Lp * 4 + 15) / 16 * 16 + align_up((size_t)V * 4 + 32, 16);
@@ -390,7 +438,8 @@ int internal_prep(const int64_t *in_len, const int64_t *tgt_len, int64_t targets
     prefer_max_carveout(k0_prep);
     k0_prep<<<1, 1024, 0, s>>>(in_len, tgt_len, targets_stride, B, T, Umax, (int *)(ws + w.hdr), (int *)(ws + w.Tb),
                                (int *)(ws + w.Ub), (int *)(ws + w.flags), (int64_t *)(ws + w.toff),
-                               (int *)(ws + w.rowstart), (int *)(ws + w.slow), (int *)(ws + w.bad));
+                               (int *)(ws + w.rowstart), (int *)(ws + w.slow), (int *)(ws + w.bad), 1,
+                               (int *)(ws + w.gstart));
     return (int)cudaGetLastError();
 }
 

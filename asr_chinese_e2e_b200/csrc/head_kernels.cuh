@@ -95,17 +95,7 @@ __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     return __uint_as_float(r);
 }
-// A hang on the GPU box is far worse than a failed run: every mbarrier wait of this kernel gives up after ~2 s.
-__device__ __forceinline__ void mbar_wait_or_trap(uint32_t bar, uint32_t parity) {
-    const long long t0 = clock64();
-    for (;;) {
-        uint32_t ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (ok) return;
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
+__device__ __forceinline__ void mbar_wait_or_trap(uint32_t bar, uint32_t parity) { mbar_wait_bounded(bar, parity); }
 // shared-memory matrix descriptor: K-major operand, rows of 128 B, SWIZZLE_128B atoms of 8 rows (1024 B apart)
 // (cute::UMMA::SmemDescriptor: start address >> 4 in [0,14), LBO >> 4 in [16,30) -- unused for swizzled K-major, 1 like
 //  CUTLASS --, SBO >> 4 in [32,46), version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64))

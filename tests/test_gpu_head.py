@@ -78,7 +78,9 @@ def test_gradient_buffer_equals_the_oracle_gradient():
     L = _lib.lib()
     enc, W, b, tg, il, tl = _case(4, 150, 64, 301, 11, 3, "var", True)
     tl[3] = 0                                        # an empty target
-    il[2] = 5                                        # infeasible: fewer frames than labels
+    tl[2] = tg.shape[1]                              # infeasible: 5 frames for 11 labels
+    tg[2] = torch.arange(7, 7 + tg.shape[1])
+    il[2] = 5
     B, T, K = enc.shape
     V = W.shape[0]
     U = tg.shape[1]
