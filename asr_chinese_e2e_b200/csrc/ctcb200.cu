@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -13,7 +14,6 @@
 #include "lattice_lin.cuh"
 #include "layout.h"
 #include "stream_kernels.cuh"
-#include "sweep_warp.cuh"
 
 using namespace ctcb200;
 
@@ -27,9 +27,8 @@ constexpr size_t kSmemBudget = 226 * 1024;   // leave 1 KB of the 227 KB opt-in 
 // launch-shape knobs (the tuned default of the kernel in question).
 enum OptId {
     OPT_PDL, OPT_LATTICE_LOG, OPT_LIN_THR, OPT_K1F_NT, OPT_K1F_NST, OPT_K1F_CPS, OPT_K1_NT, OPT_K1_NST, OPT_K1_CPS,
-    OPT_K3_NT, OPT_K3_NST, OPT_K3_CPS, OPT_CE_NST, OPT_CE_CPS, OPT_K3P_CPS, OPT_OCC_SKIP_BITS, OPT_K1F_DIRECT,
-    OPT_K1F_CARVEOUT, OPT_ZERO_IN_LATTICE, OPT_ZERO_CPS, OPT_SKIP_LATTICE, OPT_LABEL_KEEP_L2, OPT_SWEEP_WARP,
-    OPT_K1W_NW, OPT_K1W_NSLOT, OPT_COUNT
+    OPT_K3_NT, OPT_K3_NST, OPT_K3_CPS, OPT_CE_NST, OPT_CE_CPS, OPT_K3P_CPS, OPT_OCC_SKIP_BITS,
+    OPT_ZERO_IN_LATTICE, OPT_ZERO_CPS, OPT_SKIP_LATTICE, OPT_LABEL_KEEP_L2, OPT_COUNT
 };
 struct Opt { const char *name, *env; int value; };
 Opt g_opt[OPT_COUNT] = {
@@ -45,17 +44,11 @@ Opt g_opt[OPT_COUNT] = {
     {"ce_nst", "CTCB200_CE_NST", 0}, {"ce_cps", "CTCB200_CE_CPS", 0},
     {"k3p_cps", "CTCB200_K3P_CPS", 32},
     {"occ_skip_bits", "CTCB200_OCC_SKIP_BITS", 40},     // the patch skips occupancies <= 2^-bits (0: exact zeros only)
-    {"k1f_direct", "CTCB200_K1F_DIRECT", 0}, {"k1f_carveout", "CTCB200_K1F_CARVEOUT", 40},
     {"zero_in_lattice", "CTCB200_ZERO_IN_LATTICE", 0}, {"zero_cps", "CTCB200_ZERO_CPS", 2},
     {"skip_lattice", "CTCB200_DEBUG_SKIP_LATTICE", 0},  // profiling aid: time the sweep alone
     // fused sweep: evict_last for the gradient chunks the sparse patch revisits.  Measured on B200 (round 2): the patch
     // still misses L2 (104 MB of DRAM reads either way) and the sweep gets 4 us slower -> off
     {"label_keep_l2", "CTCB200_LABEL_KEEP_L2", 0},
-    // the sweep of round 2 (sweep_warp.cuh: aligned frame groups, one warp per frame, no block barriers); 0 = the
-    // round-1 kernel k1_lse_gather for every shape (it remains the fallback for odd V / odd T)
-    {"sweep_warp", "CTCB200_SWEEP_WARP", 1},
-    {"k1w_nw", "CTCB200_K1W_NW", 0},                    // consumer warps per CTA (0 = auto)
-    {"k1w_nslot", "CTCB200_K1W_NSLOT", 0},              // ring slots (0 = as many as fit)
 };
 const bool g_opt_loaded = [] {
     for (Opt &o : g_opt) {
@@ -159,10 +152,6 @@ cudaError_t launch_k1x(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
     cudaError_t e = cudaFuncSetAttribute(k1_lse_gather<NT, MAXC, EXACT, FUSED, DIRECT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
     if (e != cudaSuccess) return e;
-    if (DIRECT) {   // direct loads are staged through the L1 data array even with no_allocate: leave it room
-        const int pct = opt(OPT_K1F_CARVEOUT);
-        cudaFuncSetAttribute(k1_lse_gather<NT, MAXC, EXACT, FUSED, DIRECT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    }
     return launch_pdl(0, k1_lse_gather<NT, MAXC, EXACT, FUSED, DIRECT>, dim3(c.grid), dim3(NT), c.smem, s, a.logits, a.targets,
                       a.tnumel, a.Tb, a.Ub, a.toff, a.rowstart, a.lp_lab, a.hdr, a.B, a.T, a.V, a.Lp, a.blank, c.nst,
                       c.slot_bytes, a.grad, a.reduction, a.inv_batch, a.best, a.zero_pad_here, a.slow, a.lin_thr, a.bad,
@@ -175,10 +164,6 @@ cudaError_t launch_k1(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
 template <int NT, int MAXC, bool EXACT>
 cudaError_t launch_k1f(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
     return launch_k1x<NT, MAXC, EXACT, true>(c, s, a);
-}
-template <int NT, int MAXC, bool EXACT>
-cudaError_t launch_k1fd(const StreamCfg &c, cudaStream_t s, const K1Args &a) {
-    return launch_k1x<NT, MAXC, EXACT, true, true>(c, s, a);
 }
 template <int NT, int MAXC, bool EXACT>
 cudaError_t launch_k3(const StreamCfg &c, cudaStream_t s, const K3Args &a) {
@@ -232,40 +217,6 @@ void prefer_max_carveout(K kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
-// Frames per aligned group of the warp sweep: the smallest P with P * V * 4 a multiple of 16; 0 = not applicable
-// (odd V would need groups of four frames; T must be a multiple of P so that no group spans two utterances).
-int group_frames(int V, int T) {
-    const int P = (V % 4 == 0) ? 1 : ((V % 2 == 0) ? 2 : 0);
-    if (P == 0 || T % P != 0) return 0;
-    return P;
-}
-
-// k1w_sweep launch; returns false (and launches nothing) when the shape does not fit
-template <bool FUSED>
-bool try_launch_k1w(cudaStream_t s, const DevInfo &dev, K1wArgs a, cudaError_t *err) {
-    const int P = a.P;
-    if (P <= 0 || !opt(OPT_SWEEP_WARP)) return false;
-    const uint32_t slot = (uint32_t)align_up((size_t)P * a.V * 4, 128);
-    int nw = opt_or(OPT_K1W_NW, 4);
-    if (nw < 2) nw = 2;
-    if (nw == 7) nw = 6;
-    if (nw > KW_MAX_CONSUMERS) nw = KW_MAX_CONSUMERS;
-    const size_t fixed = 16 * 16 + (size_t)KW_MAX_CONSUMERS * a.Lp * 4 + 128;
-    int nslot = (int)((kSmemBudget - fixed) / slot);
-    if (nslot > 16) nslot = 16;
-    const int want = opt(OPT_K1W_NSLOT);
-    if (want > 0 && want < nslot) nslot = want;
-    if (nslot < nw + 1) nw = nslot - 1;
-    if (nw < 2) return false;                            // a group does not fit the ring often enough: old kernel
-    a.nslot = nslot; a.slot_bytes = slot; a.nw = nw;
-    const size_t smem = (size_t)nslot * slot + 16 * nslot + (size_t)nw * a.Lp * 4 + 64;
-    *err = cudaFuncSetAttribute(k1w_sweep<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (*err != cudaSuccess) return true;
-    prefer_max_carveout(k1w_sweep<FUSED>);
-    *err = launch_pdl(0, k1w_sweep<FUSED>, dim3(dev.sms), dim3(32 * (nw + 1)), smem, s, a);
-    return true;
-}
-
 struct FusedGrad {          // non-null grad => 2-sweep mode: the sweep writes g*softmax, k3p adds -g*occupancy
     float *grad; int reduction; float inv_batch;
     int stages;             // bit 0: prep + sweep, bit 1: lattice, bit 2: sparse patch (7 = the whole call)
@@ -313,10 +264,7 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     cudaError_t e = cudaSuccess;
     if (stages & 1) {
     prefer_max_carveout(k0_prep);
-    const int P = group_frames(V, T);
-    int *gstart = (int *)(ws + w.gstart);
-    k0_prep<<<1, 1024, 0, s>>>(in_len, tgt_len, targets_stride, B, T, Umax, hdr, Tb, Ub, flags, toff, rowstart, slow, bad,
-                               P > 0 ? P : 1, gstart);
+    k0_prep<<<1, 1024, 0, s>>>(in_len, tgt_len, targets_stride, B, T, Umax, hdr, Tb, Ub, flags, toff, rowstart, slow, bad);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
 
@@ -334,17 +282,7 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
         const K1Args a = {logits, targets, tnumel, Tb, Ub, toff, rowstart, lp_lab, hdr, B, T, V, g.Lp, blank,
                           fused ? fg->grad : nullptr, fused ? fg->reduction : 0, fused ? fg->inv_batch : 0.f,
                           want_argmax ? (int *)(ws + w.best) : nullptr, zero_in_lattice ? 0 : 1, slow, lin_thr, bad};
-        K1wArgs wa = {logits, targets, tnumel, Tb, Ub, toff, rowstart, gstart, lp_lab, hdr, B, T, V, g.Lp, blank, P,
-                      0, 0u, 0, a.grad, a.reduction, a.inv_batch, a.best, a.zero_pad_here, slow, lin_thr, bad};
-        if (fused ? try_launch_k1w<true>(s, dev, wa, &e) : try_launch_k1w<false>(s, dev, wa, &e)) {
-            // launched (or failed to launch: e) the warp sweep
-        } else if (fused && nt1 == 128 && opt(OPT_K1F_DIRECT)) {
-            // direct-load sweep (experiment): no ring -> shared memory = reduction scratch, class table, one row
-            c.nst = 0; c.slot_bytes = 0;
-            c.smem = (96 + (size_t)g.Lp * 4 + 15) / 16 * 16 + align_up((size_t)V * 4 + 32, 16);
-            c.grid = dev.sms * opt_or(OPT_K1F_CPS, 4);
-            e = STREAM_DISPATCH(launch_k1fd, 128, rounds1, exact1, c, s, a);
-        } else if (fused) {
+        if (fused) {
             if (nt1 == 64) e = STREAM_DISPATCH(launch_k1f, 64, rounds1, exact1, c, s, a);
             else e = STREAM_DISPATCH(launch_k1f, 128, rounds1, exact1, c, s, a);
         } else {
@@ -438,8 +376,7 @@ int internal_prep(const int64_t *in_len, const int64_t *tgt_len, int64_t targets
     prefer_max_carveout(k0_prep);
     k0_prep<<<1, 1024, 0, s>>>(in_len, tgt_len, targets_stride, B, T, Umax, (int *)(ws + w.hdr), (int *)(ws + w.Tb),
                                (int *)(ws + w.Ub), (int *)(ws + w.flags), (int64_t *)(ws + w.toff),
-                               (int *)(ws + w.rowstart), (int *)(ws + w.slow), (int *)(ws + w.bad), 1,
-                               (int *)(ws + w.gstart));
+                               (int *)(ws + w.rowstart), (int *)(ws + w.slow), (int *)(ws + w.bad));
     return (int)cudaGetLastError();
 }
 

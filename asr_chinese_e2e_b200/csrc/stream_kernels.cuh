@@ -31,69 +31,56 @@ __global__ void __launch_bounds__(1024) k0_prep(const int64_t *__restrict__ in_l
                                                 int *__restrict__ hdr, int *__restrict__ Tb_arr,
                                                 int *__restrict__ Ub_arr, int *__restrict__ flags,
                                                 int64_t *__restrict__ toff, int *__restrict__ rowstart,
-                                                int *__restrict__ slow, int *__restrict__ bad_arr, int P,
-                                                int *__restrict__ gstart) {
-    // three exclusive scans over the batch: valid frames (rowstart), labels (toff, 1-D targets) and aligned frame
-    // groups of P frames (gstart; the unit of work of k1w_sweep)
-    __shared__ long long s_part[3][32];
-    __shared__ long long s_carry[3];
+                                                int *__restrict__ slow, int *__restrict__ bad_arr) {
+    __shared__ long long s_part[2][32];
+    __shared__ long long s_carry[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     griddep_launch_dependents();
-    if (tid == 0) { hdr[0] = 0; hdr[1] = 0; hdr[2] = 0; hdr[3] = 0; s_carry[0] = 0; s_carry[1] = 0; s_carry[2] = 0; }
+    if (tid == 0) { hdr[0] = 0; hdr[1] = 0; hdr[2] = 0; hdr[3] = 0; s_carry[0] = 0; s_carry[1] = 0; }
     __syncthreads();
     int bad = 0;
     for (int base = 0; base < B; base += 1024) {
         const int b = base + tid;
-        long long v[3] = {0, 0, 0};
+        long long tb = 0, ub = 0;
         if (b < B) {
             long long t = in_len[b], u = tgt_len[b];
             int mybad = 0;
             if (t < 0 || t > T) { mybad |= 1; t = t < 0 ? 0 : T; }
             if (u < 0 || u > Umax) { mybad |= 2; u = u < 0 ? 0 : Umax; }
             bad |= mybad;
-            v[0] = t; v[1] = u; v[2] = (t + P - 1) / P;
+            tb = t; ub = u;
             Tb_arr[b] = (int)t; Ub_arr[b] = (int)u; flags[b] = 0; slow[b] = 0; bad_arr[b] = mybad;
         }
-        long long sc[3] = {v[0], v[1], v[2]};                     // block-wide inclusive scans
+        // block-wide inclusive scan of (tb, ub)
+        long long st = tb, su = ub;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const long long x = __shfl_up_sync(0xffffffffu, sc[q], o);
-                if (lane >= o) sc[q] += x;
-            }
+            long long a = __shfl_up_sync(0xffffffffu, st, o), c = __shfl_up_sync(0xffffffffu, su, o);
+            if (lane >= o) { st += a; su += c; }
         }
-        if (lane == 31) { s_part[0][warp] = sc[0]; s_part[1][warp] = sc[1]; s_part[2][warp] = sc[2]; }
+        if (lane == 31) { s_part[0][warp] = st; s_part[1][warp] = su; }
         __syncthreads();
         if (warp == 0) {
-            long long pp[3] = {s_part[0][lane], s_part[1][lane], s_part[2][lane]};
+            long long pt = s_part[0][lane], pu = s_part[1][lane];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const long long x = __shfl_up_sync(0xffffffffu, pp[q], o);
-                    if (lane >= o) pp[q] += x;
-                }
+                long long a = __shfl_up_sync(0xffffffffu, pt, o), c = __shfl_up_sync(0xffffffffu, pu, o);
+                if (lane >= o) { pt += a; pu += c; }
             }
-            s_part[0][lane] = pp[0]; s_part[1][lane] = pp[1]; s_part[2][lane] = pp[2];   // inclusive over warps
+            s_part[0][lane] = pt; s_part[1][lane] = pu;   // inclusive over warps
         }
         __syncthreads();
-        long long excl[3];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) excl[q] = s_carry[q] + (warp ? s_part[q][warp - 1] : 0) + sc[q] - v[q];
+        const long long wt = warp ? s_part[0][warp - 1] : 0, wu = warp ? s_part[1][warp - 1] : 0;
+        const long long ct = s_carry[0], cu = s_carry[1];
         if (b < B) {
-            rowstart[b] = (int)excl[0];
-            toff[b] = targets_stride ? (long long)b * targets_stride : excl[1];
-            gstart[b] = (int)excl[2];
+            rowstart[b] = (int)(ct + wt + st - tb);
+            toff[b] = targets_stride ? (long long)b * targets_stride : (cu + wu + su - ub);
         }
         __syncthreads();
-        if (tid == 1023) {
-#pragma unroll
-            for (int q = 0; q < 3; ++q) s_carry[q] = excl[q] + v[q];
-        }
+        if (tid == 1023) { s_carry[0] = ct + wt + st; s_carry[1] = cu + wu + su; }
         __syncthreads();
     }
-    if (tid == 0) { rowstart[B] = (int)s_carry[0]; gstart[B] = (int)s_carry[2]; }
+    if (tid == 0) rowstart[B] = (int)s_carry[0];
     if (bad) atomicOr(&hdr[0], bad);
 }
 
@@ -232,6 +219,7 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
               int nst, uint32_t slot_bytes, float *__restrict__ grad, int reduction, float inv_batch,
               int *__restrict__ best, int zero_pad_here, int *__restrict__ slow, float lin_thr,
               int *__restrict__ bad_arr, int keep_l2) {
+    static_assert(!DIRECT, "the direct-load variant of round 1 (DESIGN.md section 5) was retired with the one-barrier reduction");
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     griddep_wait();                                  // k0_prep's lengths / prefix sums
@@ -380,40 +368,29 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
             }
             if (tid == 0 || (tid == 1 && nch > 1)) rb4[tid == 0 ? 0 : nch - 1] = ve;
         }
-        float *rd = red + (i & 1) * 12;
-        mx = warp_max(mx);
-        if (lane == 0) rd[warp] = mx;
-        __syncthreads();                                   // B1: slot fully consumed
-        if (DIRECT) {
-            const float *rb = (const float *)(smem + DIRECT_ROWBUF_OFF(Lp)) + head;
-#pragma unroll
-            for (int kk = 0; kk < MAXG; ++kk)
-                if (cg[kk] >= 0) xg[kk] = rb[cg[kk]];
-        }
-        if (!DIRECT && tid == 0 && issued < nrows) {       // refill it with row i + nst
-            issue_row(logits + ((size_t)pc.b * T + pc.t) * V, V, end16, slot0 + stage * slot_bytes,
-                      bar0 + 8 * stage, 0);
-            cursor_next(pc, Tb_arr, B);
-            ++issued;
-        }
-        const float m = NT == 128 ? fmaxf(fmaxf(rd[0], rd[1]), fmaxf(rd[2], rd[3])) : fmaxf(rd[0], rd[1]);
-        const float m2 = m * kLog2e;
-        if (best != nullptr) {   // per-frame argmax (greedy CTC decode): lowest class index attaining the row maximum
+        // ---- ONE block barrier per row (round 2; two in round 1): every warp reduces against its OWN maximum first --
+        // 2^(x - max_w) and its sum need no other warp -- and publishes (max_w, sum_w, argmax_w); after the barrier each
+        // thread combines the NT/32 partials:  M = max_w max_w,  S = sum_w sum_w * 2^(max_w - M),  and rescales its
+        // warp's exponentials by 2^(max_w - M) on the way out.
+        float *rd = red + (i & 1) * 12;                    // [max_w x4][sum_w x4][argmax_w x4], double buffered
+        const float mw = warp_max(mx);
+        const float mw2 = (mw == CTC_NEG_INF ? 0.f : mw) * kLog2e;   // (a warp whose share is all -inf contributes 0)
+        if (best != nullptr) {   // per-frame argmax (greedy CTC decode): lowest class index attaining the warp maximum
             int cand = 0x7fffffff;
 #pragma unroll
             for (int k = 0; k < MAXC; ++k) {
                 const int e = 4 * (1 + tid + k * NT) - head;
-                if (v[k].w == m) cand = min(cand, e + 3);
-                if (v[k].z == m) cand = min(cand, e + 2);
-                if (v[k].y == m) cand = min(cand, e + 1);
-                if (v[k].x == m) cand = min(cand, e);
+                if (v[k].w == mw) cand = min(cand, e + 3);
+                if (v[k].z == mw) cand = min(cand, e + 2);
+                if (v[k].y == mw) cand = min(cand, e + 1);
+                if (v[k].x == mw) cand = min(cand, e);
             }
             if (tid == 0 || (tid == 1 && nch > 1)) {
                 const int e = 4 * (tid == 0 ? 0 : nch - 1) - head;
-                if (ve.w == m) cand = min(cand, e + 3);
-                if (ve.z == m) cand = min(cand, e + 2);
-                if (ve.y == m) cand = min(cand, e + 1);
-                if (ve.x == m) cand = min(cand, e);
+                if (ve.w == mw) cand = min(cand, e + 3);
+                if (ve.z == mw) cand = min(cand, e + 2);
+                if (ve.y == mw) cand = min(cand, e + 1);
+                if (ve.x == mw) cand = min(cand, e);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
@@ -422,23 +399,37 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
         float sum = 0.f;
 #pragma unroll
         for (int k = 0; k < MAXC; ++k) {
-            v[k].x = ex2f(fmaf(v[k].x, kLog2e, -m2)); v[k].y = ex2f(fmaf(v[k].y, kLog2e, -m2));
-            v[k].z = ex2f(fmaf(v[k].z, kLog2e, -m2)); v[k].w = ex2f(fmaf(v[k].w, kLog2e, -m2));
+            v[k].x = ex2f(fmaf(v[k].x, kLog2e, -mw2)); v[k].y = ex2f(fmaf(v[k].y, kLog2e, -mw2));
+            v[k].z = ex2f(fmaf(v[k].z, kLog2e, -mw2)); v[k].w = ex2f(fmaf(v[k].w, kLog2e, -mw2));
             sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
         }
         if (warp == 0) {
-            ve.x = ex2f(fmaf(ve.x, kLog2e, -m2)); ve.y = ex2f(fmaf(ve.y, kLog2e, -m2));
-            ve.z = ex2f(fmaf(ve.z, kLog2e, -m2)); ve.w = ex2f(fmaf(ve.w, kLog2e, -m2));
+            ve.x = ex2f(fmaf(ve.x, kLog2e, -mw2)); ve.y = ex2f(fmaf(ve.y, kLog2e, -mw2));
+            ve.z = ex2f(fmaf(ve.z, kLog2e, -mw2)); ve.w = ex2f(fmaf(ve.w, kLog2e, -mw2));
             sum += (ve.x + ve.y) + (ve.z + ve.w);
         }
         sum = warp_sum(sum);
-        if (lane == 0) rd[4 + warp] = sum;
-        __syncthreads();                                   // B2
-        const float tot = NT == 128 ? (rd[4] + rd[5]) + (rd[6] + rd[7]) : rd[4] + rd[5];
+        if (lane == 0) { rd[warp] = mw; rd[4 + warp] = sum; }
+        __syncthreads();                                   // the row's only barrier: slot consumed, partials visible
+        if (tid == 0 && issued < nrows) {                  // refill the slot with row i + nst
+            issue_row(logits + ((size_t)pc.b * T + pc.t) * V, V, end16, slot0 + stage * slot_bytes,
+                      bar0 + 8 * stage, 0);
+            cursor_next(pc, Tb_arr, B);
+            ++issued;
+        }
+        const float m = NT == 128 ? fmaxf(fmaxf(rd[0], rd[1]), fmaxf(rd[2], rd[3])) : fmaxf(rd[0], rd[1]);
+        const float m2 = m * kLog2e;
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) tot += rd[4 + w] * ex2f(fmaf(rd[w] == CTC_NEG_INF ? 0.f : rd[w], kLog2e, -m2));
+        const float fw = ex2f(mw2 - m2);                   // this warp's 2^(x - max_w) -> 2^(x - M)
         const float lse2 = m2 + lg2f(tot);
         if (best != nullptr && tid == 0) {
             const int *ri = (const int *)rd + 8;
-            best[(size_t)cc.b * T + cc.t] = NT == 128 ? min(min(ri[0], ri[1]), min(ri[2], ri[3])) : min(ri[0], ri[1]);
+            int bi = 0x7fffffff;
+#pragma unroll
+            for (int w = 0; w < NT / 32; ++w) if (rd[w] == m) bi = min(bi, ri[w]);
+            best[(size_t)cc.b * T + cc.t] = bi;
         }
         float *frame = lp_lab + ((size_t)cc.b * T + cc.t) * Lp;
 #pragma unroll
@@ -461,7 +452,7 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
         }
         if (FUSED) {
             // dense gradient: g * softmax = 2^(x-max) * g / sum, from the registers that still hold the row
-            const float sc = g * __frcp_rn(tot);           // softmax = 2^(x-max) / sum: no lse rounding involved
+            const float sc = g * fw * __frcp_rn(tot);      // softmax = 2^(x-max_w) * 2^(max_w-M) / sum: no lse rounding involved
             float *orow = grad + ((size_t)cc.b * T + cc.t) * V;
             float4 *g4 = (float4 *)((uintptr_t)orow & ~(uintptr_t)15);
             const uint32_t lm = head == 0 ? lmask[0] : (head == 1 ? lmask[1] : (head == 2 ? lmask[2] : lmask[3]));
