@@ -256,11 +256,13 @@ class _CTCLossB200Fn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, logits, targets, input_lengths, target_lengths, blank, reduction, zero_infinity,
-                inv_batch, max_target_length, fused, chunks, decode, lattice_event=None):
+                inv_batch, max_target_length, fused, chunks, decode, lattice_event=None, grad_mode=True):
         x, tg, stride, il, tl, B, T, V, umax = _prepare(logits, targets, input_lengths, target_lengths,
                                                         blank, max_target_length)
         L = _lib.lib()
-        need_grad = ctx.needs_input_grad[0]
+        # (needs_input_grad ignores torch.no_grad(): an evaluation pass over tensors that require grad must still take
+        #  the loss-only path -- grad_mode is torch.is_grad_enabled() at the call site)
+        need_grad = bool(ctx.needs_input_grad[0] and grad_mode)
         fused = bool(need_grad and fused)
         two_sweep = _CFG["two_sweep"]
         red = _RED[reduction]
@@ -373,7 +375,7 @@ class _CTCLossB200Fn(torch.autograd.Function):
                 _lib.check(L.ctcb200_rescale_grad(grad.data_ptr(), go.data_ptr(), 1 if red == 0 else 0,
                                                   ones.data_ptr(), scratch.data_ptr(), B, T, V, stream),
                            "ctcb200_rescale_grad")
-            return (grad,) + (None,) * 12
+            return (grad,) + (None,) * 13
         x, tg, ws = ctx.saved_tensors[-3:]
         grad = torch.empty_like(x)
         xs = x.element_size() * T * V
@@ -386,7 +388,7 @@ class _CTCLossB200Fn(torch.autograd.Function):
                                               go.data_ptr() + lo * gs, 1 if red == 0 else 0, red, inv_b, n, T, V,
                                               umax, blank, zi, grad.data_ptr() + lo * xs,
                                               ws.data_ptr() + wo, wb, stream), "ctcb200_backward")
-        return (grad,) + (None,) * 12
+        return (grad,) + (None,) * 13
 
 
 def ctc_loss_b200(logits, targets, input_lengths, target_lengths, blank: int = 0,
@@ -417,7 +419,8 @@ def ctc_loss_b200(logits, targets, input_lengths, target_lengths, blank: int = 0
         chunks = 1
     ev = [lattice_event, False] if lattice_event is not None else None
     out = _CTCLossB200Fn.apply(logits, targets, input_lengths, target_lengths, blank, reduction,
-                               zero_infinity, inv_batch, max_target_length, fused, chunks, decode, ev)
+                               zero_infinity, inv_batch, max_target_length, fused, chunks, decode, ev,
+                               torch.is_grad_enabled())
     if ev is not None and not ev[1]:
         lattice_event.record(torch.cuda.current_stream(out.device))   # paths that do not split the call
     return out

@@ -30,7 +30,7 @@ _PREC = {"3xtf32": 0, "tf32": 1}
 class _CTCHeadLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, enc, weight, bias, targets, input_lengths, target_lengths, blank, reduction, zero_infinity,
-                inv_batch, precision, max_target_length):
+                inv_batch, precision, max_target_length, grad_mode=True):
         for name, x in (("enc", enc), ("weight", weight)):
             if not (torch.is_tensor(x) and x.is_cuda):
                 raise _lib.CtcB200Error(f"ctc_head_loss_b200 needs CUDA tensors ({name}): the hot path has no CPU fallback")
@@ -61,7 +61,7 @@ class _CTCHeadLossFn(torch.autograd.Function):
                 tg = tg.new_zeros(1)
         L = _lib.lib()
         prec = _PREC[precision]
-        need_grad = any(ctx.needs_input_grad[:3])
+        need_grad = bool(any(ctx.needs_input_grad[:3]) and grad_mode)     # (needs_input_grad ignores torch.no_grad())
         red = _RED[reduction]
         flags = int(bool(zero_infinity)) | (4 if _CFG["lattice_log"] else 0)
         inv_b = float(inv_batch) if inv_batch is not None else 1.0 / max(B, 1)
@@ -109,7 +109,7 @@ class _CTCHeadLossFn(torch.autograd.Function):
             g_b = d.sum(0)
             if go is not None:
                 g_b = g_b * go
-        return (g_enc, g_w, g_b) + (None,) * 9
+        return (g_enc, g_w, g_b) + (None,) * 10
 
 
 def ctc_head_loss_b200(enc, weight, bias, targets, input_lengths, target_lengths, blank: int = 0,
@@ -122,4 +122,4 @@ def ctc_head_loss_b200(enc, weight, bias, targets, input_lengths, target_lengths
     if precision not in _PREC:
         raise ValueError(f"precision must be one of {list(_PREC)}")
     return _CTCHeadLossFn.apply(enc, weight, bias, targets, input_lengths, target_lengths, blank, reduction,
-                                zero_infinity, inv_batch, precision, max_target_length)
+                                zero_infinity, inv_batch, precision, max_target_length, torch.is_grad_enabled())

@@ -282,3 +282,23 @@ def test_forward_backward_is_cuda_graph_capturable():
                          zero_infinity=True)
         assert abs(loss.item() - rl.item()) <= 1e-5 * abs(rl.item())
         assert (x.grad.cpu() - rg).abs().max().item() <= 1e-4
+
+
+def test_no_grad_takes_the_loss_only_path_even_if_the_logits_require_grad():
+    """Evaluation (Trainer11.evaluate runs model.iterate under torch.no_grad()) must not pay for a gradient: autograd's
+    needs_input_grad ignores the grad mode, so the op checks it itself -- visible as no [B,T,V] buffer being allocated."""
+    from asr_chinese_e2e_b200 import ctc_loss_b200
+    c = make_case(32, 200, 4234, 20, 9)
+    x = c["logits"].cuda().requires_grad_(True)
+    args = [c[k].cuda() for k in ("targets", "input_lengths", "target_lengths")]
+    with torch.no_grad():
+        ctc_loss_b200(x, *args)                                    # warm-up (library load, workspace sizes)
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        loss = ctc_loss_b200(x, *args)
+        torch.cuda.synchronize()
+        assert torch.cuda.max_memory_allocated() - base < x.numel() * 4      # no gradient slab
+    assert not loss.requires_grad
+    loss2 = ctc_loss_b200(x, *args)
+    assert loss2.requires_grad and torch.allclose(loss, loss2.detach(), rtol=1e-6)
