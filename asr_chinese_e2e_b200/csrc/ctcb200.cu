@@ -34,8 +34,10 @@ struct Opt { const char *name, *env; int value; };
 Opt g_opt[OPT_COUNT] = {
     // bit 0: sweep after prep (measured: +70 us per step in a back-to-back loop; also not safe as is: the sweep reads
     // k0_prep's arrays through const __restrict__ pointers, i.e. possibly non-coherent loads), bit 1: lattice after
-    // sweep, bit 2: patch after lattice (its class tables are built while the lattice drains: -5 us)
-    {"pdl", "CTCB200_PDL", 6},
+    // sweep, bit 2: patch after lattice (its class tables are built while the lattice drains: -5 us), bit 3: also when
+    // the patch is launched as a stage of its own behind an event record (sharded_ctc_loss splits the call there so
+    // that its all-reduce can start; griddepcontrol.wait keeps it correct whatever the runtime makes of the attribute)
+    {"pdl", "CTCB200_PDL", 14},
     {"lattice_log", "CTCB200_LATTICE_LOG", 0},          // 1: log-space recursion for every utterance
     {"lin_thr", "CTCB200_LIN_THR", 0},                  // range limit of the linear-domain lattice (bits; 0 = auto)
     {"k1f_nt", "CTCB200_K1F_NT", 0}, {"k1f_nst", "CTCB200_K1F_NST", 0}, {"k1f_cps", "CTCB200_K1F_CPS", 0},
@@ -322,7 +324,7 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
         const float occ_skip = skip_bits > 0 ? ldexpf(1.f, -skip_bits) : 0.f;
         const size_t smem = 2 * (size_t)g.Lp * 4;
         prefer_max_carveout(k3p_patch<64>);
-        e = launch_pdl((stages & 2) ? 2 : -1, k3p_patch<64>, dim3(dev.sms * (per < 1 ? 1 : per)), dim3(64), smem, s, targets, tnumel, Tb, Ub, toff,
+        e = launch_pdl((stages & 2) ? 2 : 3, k3p_patch<64>, dim3(dev.sms * (per < 1 ? 1 : per)), dim3(64), smem, s, targets, tnumel, Tb, Ub, toff,
                        flags, rowstart, gam, fg->grad, fg->reduction, fg->inv_batch, B, T, V, g.Lp, blank, zero_infinity, occ_skip, bad);
     }
     return (int)e;

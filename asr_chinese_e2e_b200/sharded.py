@@ -40,6 +40,20 @@ def combine_sharded_mean(local_sum: torch.Tensor, local_count: int, group=None) 
     return local + (buf[0] * inv - local.detach())            # value: global mean
 
 
+class _GlobalValueLocalGrad(torch.autograd.Function):
+    """value: the all-reduced global mean (`total`, returned as is -- no kernel); gradient: d/d local = 1.
+    Replaces `local + (total - local.detach())`, three elementwise launches (~9 us per step measured on B200) that sat
+    on the critical path of every sharded step."""
+
+    @staticmethod
+    def forward(ctx, local, total):
+        return total.view_as(local)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
 _SIDE = {}
 
 
@@ -58,6 +72,10 @@ def combine_equal_shards(local_contrib: torch.Tensor, group=None, ready_event=No
     behind the kernels with no host sync."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local_contrib
+    world = dist.get_world_size(group)
+    # one collective, nothing else: the division by `world` (grad_reduce='mean') is NCCL's own AVG
+    avg = abs(value_scale * world - 1.0) < 1e-12 and local_contrib.is_cuda
+    op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
     if ready_event is not None and local_contrib.is_cuda:
         # The value is final at `ready_event` (after the lattice kernel) while the current stream still has the
         # sparse gradient patch queued: run the all-reduce on a side stream behind that event, so that its
@@ -67,15 +85,15 @@ def combine_equal_shards(local_contrib: torch.Tensor, group=None, ready_event=No
         side.wait_event(ready_event)
         with torch.cuda.stream(side):
             tot = local_contrib.detach().clone()
-            dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(tot, op=op, group=group)
         tot.record_stream(main)
         main.wait_stream(side)
     else:
         tot = local_contrib.detach().clone()
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
-    if value_scale != 1.0:
+        dist.all_reduce(tot, op=op, group=group)
+    if not avg and value_scale != 1.0:
         tot = tot * value_scale
-    return local_contrib + (tot - local_contrib.detach())     # value: global mean; gradient: d/d local = 1
+    return _GlobalValueLocalGrad.apply(local_contrib, tot)    # value: global mean; gradient: d/d local = 1
 
 
 def sharded_ctc_loss(logits, targets, input_lengths, target_lengths, blank: int = 0,
