@@ -14,6 +14,7 @@
 #include "lattice_lin.cuh"
 #include "layout.h"
 #include "stream_kernels.cuh"
+#include "sweep_direct.cuh"
 
 using namespace ctcb200;
 
@@ -28,7 +29,7 @@ constexpr size_t kSmemBudget = 226 * 1024;   // leave 1 KB of the 227 KB opt-in 
 enum OptId {
     OPT_PDL, OPT_LATTICE_LOG, OPT_LIN_THR, OPT_K1F_NT, OPT_K1F_NST, OPT_K1F_CPS, OPT_K1_NT, OPT_K1_NST, OPT_K1_CPS,
     OPT_K3_NT, OPT_K3_NST, OPT_K3_CPS, OPT_CE_NST, OPT_CE_CPS, OPT_K3P_CPS, OPT_OCC_SKIP_BITS,
-    OPT_ZERO_IN_LATTICE, OPT_ZERO_CPS, OPT_SKIP_LATTICE, OPT_LABEL_KEEP_L2, OPT_COUNT
+    OPT_ZERO_IN_LATTICE, OPT_ZERO_CPS, OPT_SKIP_LATTICE, OPT_LABEL_KEEP_L2, OPT_SWEEP_DIRECT, OPT_K1D_CPS, OPT_COUNT
 };
 struct Opt { const char *name, *env; int value; };
 Opt g_opt[OPT_COUNT] = {
@@ -51,6 +52,11 @@ Opt g_opt[OPT_COUNT] = {
     // fused sweep: evict_last for the gradient chunks the sparse patch revisits.  Measured on B200 (round 2): the patch
     // still misses L2 (104 MB of DRAM reads either way) and the sweep gets 4 us slower -> off
     {"label_keep_l2", "CTCB200_LABEL_KEEP_L2", 0},
+    // 1: the alternative sweep kernel of round 2 (sweep_direct.cuh: aligned frame groups, direct LDG.128 loads into
+    // registers, one barrier per group, no shared-memory ring).  Measured on B200: the same speed as the TMA-ring
+    // kernel k1_lse_gather (C2 full lengths 0.618 vs 0.619 ms), so the ring kernel stays the default
+    {"sweep_direct", "CTCB200_SWEEP_DIRECT", 0},
+    {"k1d_cps", "CTCB200_K1D_CPS", 0},                  // CTAs per SM of k1d_sweep (0 = 4, or 2 for wide vocabularies)
 };
 const bool g_opt_loaded = [] {
     for (Opt &o : g_opt) {
@@ -219,6 +225,35 @@ void prefer_max_carveout(K kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
+// Frames per aligned group of the direct sweep: the smallest P with P * V * 4 a multiple of 16; 0 = not applicable
+// (odd V would need groups of four frames; T must be a multiple of P so that no group spans two utterances).
+int group_frames(int V, int T) {
+    const int P = (V % 4 == 0) ? 1 : ((V % 2 == 0) ? 2 : 0);
+    if (P == 0 || T % P != 0) return 0;
+    return P;
+}
+
+template <int MAXC, bool FUSED>
+cudaError_t launch_k1d(cudaStream_t s, int sms, const K1dArgs &a) {
+    // default carve-out (small shared memory, large L1): direct loads are staged through the L1 data array
+    cudaFuncSetAttribute(k1d_sweep<MAXC, FUSED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutDefault);
+    const int cps = opt_or(OPT_K1D_CPS, MAXC <= 17 ? 4 : 2);
+    return launch_pdl(0, k1d_sweep<MAXC, FUSED>, dim3(sms * cps), dim3(128), 0, s, a);
+}
+// k1d_sweep launch; returns false (and launches nothing) when the shape does not fit
+template <bool FUSED>
+bool try_launch_k1d(cudaStream_t s, const DevInfo &dev, const K1dArgs &a, cudaError_t *err) {
+    if (a.P <= 0 || !opt(OPT_SWEEP_DIRECT) || a.Lp > 264) return false;
+    if (((uintptr_t)a.logits & 15) || (FUSED && ((uintptr_t)a.grad & 15))) return false;
+    const int nch = a.P * a.V / 4;
+    if (nch <= 128 * 5) *err = launch_k1d<5, FUSED>(s, dev.sms, a);
+    else if (nch <= 128 * 9) *err = launch_k1d<9, FUSED>(s, dev.sms, a);
+    else if (nch <= 128 * 17) *err = launch_k1d<17, FUSED>(s, dev.sms, a);
+    else if (nch <= 128 * 33) *err = launch_k1d<33, FUSED>(s, dev.sms, a);
+    else return false;
+    return true;
+}
+
 struct FusedGrad {          // non-null grad => 2-sweep mode: the sweep writes g*softmax, k3p adds -g*occupancy
     float *grad; int reduction; float inv_batch;
     int stages;             // bit 0: prep + sweep, bit 1: lattice, bit 2: sparse patch (7 = the whole call)
@@ -266,7 +301,10 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     cudaError_t e = cudaSuccess;
     if (stages & 1) {
     prefer_max_carveout(k0_prep);
-    k0_prep<<<1, 1024, 0, s>>>(in_len, tgt_len, targets_stride, B, T, Umax, hdr, Tb, Ub, flags, toff, rowstart, slow, bad);
+    const int P = group_frames(V, T);
+    int *gstart = (int *)(ws + w.gstart);
+    k0_prep<<<1, 1024, 0, s>>>(in_len, tgt_len, targets_stride, B, T, Umax, hdr, Tb, Ub, flags, toff, rowstart, slow, bad,
+                               P > 0 ? P : 1, gstart);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
 
@@ -284,7 +322,11 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
         const K1Args a = {logits, targets, tnumel, Tb, Ub, toff, rowstart, lp_lab, hdr, B, T, V, g.Lp, blank,
                           fused ? fg->grad : nullptr, fused ? fg->reduction : 0, fused ? fg->inv_batch : 0.f,
                           want_argmax ? (int *)(ws + w.best) : nullptr, zero_in_lattice ? 0 : 1, slow, lin_thr, bad};
-        if (fused) {
+        const K1dArgs da = {logits, targets, tnumel, Tb, Ub, toff, rowstart, gstart, lp_lab, hdr, B, T, V, g.Lp, blank, P,
+                            a.grad, a.reduction, a.inv_batch, a.best, a.zero_pad_here, slow, lin_thr, bad};
+        if (fused ? try_launch_k1d<true>(s, dev, da, &e) : try_launch_k1d<false>(s, dev, da, &e)) {
+            // the direct sweep was launched (or failed to launch: e)
+        } else if (fused) {
             if (nt1 == 64) e = STREAM_DISPATCH(launch_k1f, 64, rounds1, exact1, c, s, a);
             else e = STREAM_DISPATCH(launch_k1f, 128, rounds1, exact1, c, s, a);
         } else {
@@ -378,7 +420,8 @@ int internal_prep(const int64_t *in_len, const int64_t *tgt_len, int64_t targets
     prefer_max_carveout(k0_prep);
     k0_prep<<<1, 1024, 0, s>>>(in_len, tgt_len, targets_stride, B, T, Umax, (int *)(ws + w.hdr), (int *)(ws + w.Tb),
                                (int *)(ws + w.Ub), (int *)(ws + w.flags), (int64_t *)(ws + w.toff),
-                               (int *)(ws + w.rowstart), (int *)(ws + w.slow), (int *)(ws + w.bad));
+                               (int *)(ws + w.rowstart), (int *)(ws + w.slow), (int *)(ws + w.bad), 1,
+                               (int *)(ws + w.gstart));
     return (int)cudaGetLastError();
 }
 

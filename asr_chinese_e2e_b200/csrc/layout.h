@@ -59,6 +59,7 @@ struct Workspace {
                       //          utterance's nll and gradient are poisoned with NaN (F.ctc_loss raises on these)
     size_t toff;      // int64[B] element offset of utterance b's labels in `targets`
     size_t rowstart;  // int[B+1] exclusive prefix sum of Tb (valid-frame numbering)
+    size_t gstart;    // int[B+1] exclusive prefix sum of ceil(Tb / P): numbering of the aligned frame groups (k1d_sweep)
     size_t lp_lab;    // float[B*T*Lp]
     size_t gam;       // float[B*T*Lp]
     size_t ab;        // stored alpha/beta halves: B blocks of ab_utt bytes (see lin_ab_utt_bytes)
@@ -80,6 +81,7 @@ static inline Workspace workspace_layout(int B, int T, const Geom &g) {
     w.bad = o;       o += align_up(sizeof(int) * b);
     w.toff = o;      o += align_up(sizeof(int64_t) * b);
     w.rowstart = o;  o += align_up(sizeof(int) * (b + 1));
+    w.gstart = o;    o += align_up(sizeof(int) * (b + 1));
     w.lp_lab = o;    o += align_up(sizeof(float) * b * T * g.Lp);
     w.gam = o;       o += align_up(sizeof(float) * b * T * g.Lp);
     w.ab_utt = lin_ab_utt_bytes(T, g);

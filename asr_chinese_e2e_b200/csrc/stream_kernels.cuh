@@ -31,56 +31,69 @@ __global__ void __launch_bounds__(1024) k0_prep(const int64_t *__restrict__ in_l
                                                 int *__restrict__ hdr, int *__restrict__ Tb_arr,
                                                 int *__restrict__ Ub_arr, int *__restrict__ flags,
                                                 int64_t *__restrict__ toff, int *__restrict__ rowstart,
-                                                int *__restrict__ slow, int *__restrict__ bad_arr) {
-    __shared__ long long s_part[2][32];
-    __shared__ long long s_carry[2];
+                                                int *__restrict__ slow, int *__restrict__ bad_arr, int P,
+                                                int *__restrict__ gstart) {
+    // three exclusive scans over the batch: valid frames (rowstart), labels (toff, 1-D targets) and aligned frame
+    // groups of P frames (gstart; the unit of work of k1d_sweep)
+    __shared__ long long s_part[3][32];
+    __shared__ long long s_carry[3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     griddep_launch_dependents();
-    if (tid == 0) { hdr[0] = 0; hdr[1] = 0; hdr[2] = 0; hdr[3] = 0; s_carry[0] = 0; s_carry[1] = 0; }
+    if (tid == 0) { hdr[0] = 0; hdr[1] = 0; hdr[2] = 0; hdr[3] = 0; s_carry[0] = 0; s_carry[1] = 0; s_carry[2] = 0; }
     __syncthreads();
     int bad = 0;
     for (int base = 0; base < B; base += 1024) {
         const int b = base + tid;
-        long long tb = 0, ub = 0;
+        long long v[3] = {0, 0, 0};
         if (b < B) {
             long long t = in_len[b], u = tgt_len[b];
             int mybad = 0;
             if (t < 0 || t > T) { mybad |= 1; t = t < 0 ? 0 : T; }
             if (u < 0 || u > Umax) { mybad |= 2; u = u < 0 ? 0 : Umax; }
             bad |= mybad;
-            tb = t; ub = u;
+            v[0] = t; v[1] = u; v[2] = (t + P - 1) / P;
             Tb_arr[b] = (int)t; Ub_arr[b] = (int)u; flags[b] = 0; slow[b] = 0; bad_arr[b] = mybad;
         }
-        // block-wide inclusive scan of (tb, ub)
-        long long st = tb, su = ub;
+        long long sc[3] = {v[0], v[1], v[2]};                     // block-wide inclusive scans
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            long long a = __shfl_up_sync(0xffffffffu, st, o), c = __shfl_up_sync(0xffffffffu, su, o);
-            if (lane >= o) { st += a; su += c; }
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const long long x = __shfl_up_sync(0xffffffffu, sc[q], o);
+                if (lane >= o) sc[q] += x;
+            }
         }
-        if (lane == 31) { s_part[0][warp] = st; s_part[1][warp] = su; }
+        if (lane == 31) { s_part[0][warp] = sc[0]; s_part[1][warp] = sc[1]; s_part[2][warp] = sc[2]; }
         __syncthreads();
         if (warp == 0) {
-            long long pt = s_part[0][lane], pu = s_part[1][lane];
+            long long pp[3] = {s_part[0][lane], s_part[1][lane], s_part[2][lane]};
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                long long a = __shfl_up_sync(0xffffffffu, pt, o), c = __shfl_up_sync(0xffffffffu, pu, o);
-                if (lane >= o) { pt += a; pu += c; }
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const long long x = __shfl_up_sync(0xffffffffu, pp[q], o);
+                    if (lane >= o) pp[q] += x;
+                }
             }
-            s_part[0][lane] = pt; s_part[1][lane] = pu;   // inclusive over warps
+            s_part[0][lane] = pp[0]; s_part[1][lane] = pp[1]; s_part[2][lane] = pp[2];   // inclusive over warps
         }
         __syncthreads();
-        const long long wt = warp ? s_part[0][warp - 1] : 0, wu = warp ? s_part[1][warp - 1] : 0;
-        const long long ct = s_carry[0], cu = s_carry[1];
+        long long excl[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) excl[q] = s_carry[q] + (warp ? s_part[q][warp - 1] : 0) + sc[q] - v[q];
         if (b < B) {
-            rowstart[b] = (int)(ct + wt + st - tb);
-            toff[b] = targets_stride ? (long long)b * targets_stride : (cu + wu + su - ub);
+            rowstart[b] = (int)excl[0];
+            toff[b] = targets_stride ? (long long)b * targets_stride : excl[1];
+            gstart[b] = (int)excl[2];
         }
         __syncthreads();
-        if (tid == 1023) { s_carry[0] = ct + wt + st; s_carry[1] = cu + wu + su; }
+        if (tid == 1023) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) s_carry[q] = excl[q] + v[q];
+        }
         __syncthreads();
     }
-    if (tid == 0) rowstart[B] = (int)s_carry[0];
+    if (tid == 0) { rowstart[B] = (int)s_carry[0]; gstart[B] = (int)s_carry[2]; }
     if (bad) atomicOr(&hdr[0], bad);
 }
 

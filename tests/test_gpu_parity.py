@@ -399,3 +399,27 @@ def test_skipping_negligible_occupancies_changes_nothing_measurable():
         _lib.set_option("occ_skip_bits", 40)
     diff = (outs[0] - outs[1]).abs().max().item()
     assert diff <= 2.0 ** -39                                   # occupancy + at most half an ulp of the result
+
+
+def test_direct_sweep_option_is_parity_green():
+    """The alternative sweep kernel (sweep_direct.cuh: aligned frame groups, direct loads, one barrier per group) behind
+    the `sweep_direct` option: same parity suite, including an odd last frame, infeasible utterances, the non-fused
+    paths and V % 4 == 0; shapes it does not cover (odd V, odd T) silently use the ring kernel."""
+    from asr_chinese_e2e_b200 import _lib
+    try:
+        _lib.set_option("sweep_direct", 1)
+        for (B, T, V, U, seed) in ((7, 62, 54, 13, 21), (5, 40, 64, 7, 22), (3, 200, 4234, 30, 23), (4, 31, 53, 6, 24)):
+            c = make_case(B, T, V, U, seed, dist="D2", n_infeasible=1, n_partial=1)
+            c["input_lengths"][0] = T - 1 if T % 2 == 0 else T            # an odd number of valid frames
+            check_case(c, True, f"direct sweep V={V} T={T}")
+        c = make_config("C1")
+        check_case(c, False, "direct sweep C1")
+        from asr_chinese_e2e_b200 import ctc_greedy_cer_b200
+        from asr_chinese_e2e_b200.joint import greedy_ctc_ids
+        c = make_case(5, 200, 4234, 30, 77, dist="D2")
+        _, info = ctc_greedy_cer_b200(c["logits"].cuda(), c["targets"].cuda(), c["input_lengths"].cuda(), c["target_lengths"].cuda())
+        want = greedy_ctc_ids(c["logits"], c["input_lengths"])
+        for b in range(5):
+            assert info["hyp"][b, : int(info["hyp_len"][b])].tolist() == want[b]
+    finally:
+        _lib.set_option("sweep_direct", 0)
