@@ -14,8 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(_HERE, "libctcb200.so")
 SOURCES = ["ctcb200.cu", "head.cu"]
-HEADERS = ["ptx.cuh", "layout.h", "stream_kernels.cuh", "lattice_kernel.cuh", "lattice_lin.cuh", "ce_kernel.cuh", "decode_kernel.cuh",
-           "head_kernels.cuh", "internal.h", os.path.join("..", "..", "include", "ctcb200.h")]
+HEADERS = ["ptx.cuh", "layout.h", "stream_kernels.cuh", "sweep_direct.cuh", "lattice_kernel.cuh", "lattice_lin.cuh", "ce_kernel.cuh",
+           "decode_kernel.cuh", "head_kernels.cuh", "gemm_tf32x3.cuh", "internal.h", os.path.join("..", "..", "include", "ctcb200.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-diag-suppress", "128"]
@@ -81,6 +81,8 @@ SIGNATURES = {
     "ctcb200_head_loss": (_i, [_p, _p, _p, _p, _i64, _i64, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
     "ctcb200_head_loss_grad": (_i, [_p, _p, _p, _p, _i64, _i64, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p,
                                     _p, _i64, _p, _sz, _p]),
+    "ctcb200_head_param_grads_workspace_bytes": (_i, [_i, _i, ctypes.POINTER(_sz)]),
+    "ctcb200_head_param_grads": (_i, [_p, _i64, _p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
     "ctcb200_read_status": (_i, [_p, ctypes.POINTER(_i), _p]),
     "ctcb200_read_lattice_stats": (_i, [_p, ctypes.POINTER(_i), _p]),
 }
@@ -116,6 +118,12 @@ def check(code: int, what: str) -> None:
 def head_workspace_bytes(B: int, T: int, V: int, K: int, Umax: int, precision: int) -> int:
     out = _sz(0)
     check(lib().ctcb200_head_workspace_bytes(B, T, V, K, Umax, precision, ctypes.byref(out)), "ctcb200_head_workspace_bytes")
+    return int(out.value)
+
+
+def head_param_grads_workspace_bytes(V: int, K: int) -> int:
+    out = _sz(0)
+    check(lib().ctcb200_head_param_grads_workspace_bytes(V, K, ctypes.byref(out)), "ctcb200_head_param_grads_workspace_bytes")
     return int(out.value)
 
 

@@ -29,7 +29,8 @@ constexpr size_t kSmemBudget = 226 * 1024;   // leave 1 KB of the 227 KB opt-in 
 enum OptId {
     OPT_PDL, OPT_LATTICE_LOG, OPT_LIN_THR, OPT_K1F_NT, OPT_K1F_NST, OPT_K1F_CPS, OPT_K1_NT, OPT_K1_NST, OPT_K1_CPS,
     OPT_K3_NT, OPT_K3_NST, OPT_K3_CPS, OPT_CE_NST, OPT_CE_CPS, OPT_K3P_CPS, OPT_OCC_SKIP_BITS,
-    OPT_ZERO_IN_LATTICE, OPT_ZERO_CPS, OPT_SKIP_LATTICE, OPT_LABEL_KEEP_L2, OPT_SWEEP_DIRECT, OPT_K1D_CPS, OPT_COUNT
+    OPT_ZERO_IN_LATTICE, OPT_ZERO_CPS, OPT_SKIP_LATTICE, OPT_LABEL_KEEP_L2, OPT_SWEEP_DIRECT, OPT_K1D_CPS,
+    OPT_G3_SWZ, OPT_G3_LBO, OPT_G3_SBO, OPT_G3_LAYOUT, OPT_COUNT
 };
 struct Opt { const char *name, *env; int value; };
 Opt g_opt[OPT_COUNT] = {
@@ -57,6 +58,10 @@ Opt g_opt[OPT_COUNT] = {
     // kernel k1_lse_gather (C2 full lengths 0.618 vs 0.619 ms), so the ring kernel stays the default
     {"sweep_direct", "CTCB200_SWEEP_DIRECT", 0},
     {"k1d_cps", "CTCB200_K1D_CPS", 0},                  // CTAs per SM of k1d_sweep (0 = 4, or 2 for wide vocabularies)
+    // k_gemm3 (gemm_tf32x3.cuh), MN-major operand tiles: tensor-map swizzle enum, descriptor LBO / SBO (bytes) and layout
+    // type (0 = the kernel's defaults: SWIZZLE_128B_ATOM_32B boxes, LBO 4096, SBO 512, layout SWIZZLE_128B_BASE32B)
+    {"g3_swz", "CTCB200_G3_SWZ", 0}, {"g3_lbo", "CTCB200_G3_LBO", 0}, {"g3_sbo", "CTCB200_G3_SBO", 0},
+    {"g3_layout", "CTCB200_G3_LAYOUT", 0},
 };
 const bool g_opt_loaded = [] {
     for (Opt &o : g_opt) {
@@ -299,15 +304,16 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     // longer -- any co-resident memory traffic doubles the latency-bound lattice -- so nothing is gained.
     const bool zero_in_lattice = fused && stages == 7 && opt(OPT_ZERO_IN_LATTICE);
     cudaError_t e = cudaSuccess;
-    if (stages & 1) {
-    prefer_max_carveout(k0_prep);
     const int P = group_frames(V, T);
     int *gstart = (int *)(ws + w.gstart);
+    if (stages & (1 | 8)) {      // prep (stage bit 0 = prep + sweep; bit 3 = prep alone, bit 4 = sweep alone: profiling)
+    prefer_max_carveout(k0_prep);
     k0_prep<<<1, 1024, 0, s>>>(in_len, tgt_len, targets_stride, B, T, Umax, hdr, Tb, Ub, flags, toff, rowstart, slow, bad,
                                P > 0 ? P : 1, gstart);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-
+    }
+    if (stages & (1 | 16)) {
     StreamCfg c;
     int nt1, rounds1;
     bool exact1;
@@ -408,6 +414,8 @@ float internal_lin_thr(const Geom &g, int flags) {
     const int thr_env = opt(OPT_LIN_THR);
     return lattice_mode ? 1.f : -(float)(thr_env > 0 ? thr_env : 900 / (lin_tile_frames(g.NS) + g.NS / 2));
 }
+
+int internal_g3_opt(int which) { return opt((OptId)(OPT_G3_SWZ + which)); }
 
 float internal_occ_skip() {
     const int skip_bits = opt(OPT_OCC_SKIP_BITS);
@@ -532,7 +540,7 @@ int ctcb200_loss_grad_stages(int stages, const float *logits, const int64_t *tar
     if (!grad_logits) return CTCB200_ERR_NULL;
     if ((uintptr_t)grad_logits & 15) return CTCB200_ERR_ALIGN;
     if (reduction < 0 || reduction > 2) return CTCB200_ERR_REDUCTION;
-    if (stages < 1 || stages > 7) return CTCB200_ERR_SHAPE;
+    if (stages < 1 || stages > 31) return CTCB200_ERR_SHAPE;
     const FusedGrad fg = {grad_logits, reduction, inv_batch, stages};
     return forward_impl(true, &fg, logits, targets, targets_stride, targets_numel, in_len, tgt_len, B, T, V, Umax,
                         blank, zero_infinity, nll, loss_sums, workspace, workspace_bytes, stream, nullptr);

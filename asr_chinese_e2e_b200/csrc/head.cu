@@ -5,7 +5,10 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
+#include "gemm_tf32x3.cuh"
 #include "head_kernels.cuh"
 #include "internal.h"
 #include "layout.h"
@@ -34,6 +37,15 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
+// cuTensorMapEncodeTiled needs a current driver context in the CALLING thread (CUDA_ERROR_INVALID_CONTEXT otherwise):
+// torch's autograd worker threads have a current device but may not have touched the runtime yet, so bind the primary
+// context of the current device here (cudaSetDevice does that since CUDA 12)
+int ensure_context() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaSetDevice(dev) != cudaSuccess) return CTCB200_ERR_NO_DEVICE;
+    return 0;
+}
+
 // fp32 matrix [rows, K] row-major (K contiguous) -> boxes of box_rows x 32 floats (128 B), SWIZZLE_128B; rows past the
 // end read as zeros
 int make_map(CUtensorMap *m, const float *base, int64_t rows, int K, int box_rows) {
@@ -47,6 +59,40 @@ int make_map(CUtensorMap *m, const float *base, int64_t rows, int K, int box_row
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : CTCB200_ERR_SHAPE;
+}
+
+// fp32 matrix [rows, inner] with a row pitch (floats) -> boxes of box_rows x 32 floats, zero fill outside.  K-major
+// operand tiles (mn = false) use SWIZZLE_128B, MN-major ones SWIZZLE_128B_ATOM_32B (gemm_tf32x3.cuh)
+int make_map_pitched(CUtensorMap *m, const float *base, int64_t rows, int64_t inner, int64_t pitch, int box_rows, bool mn) {
+    EncodeTiledFn f = encode_fn();
+    if (!f) return CTCB200_ERR_NO_DEVICE;
+    const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUtensorMapSwizzle swz = mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+    if (mn && internal_g3_opt(0) > 0) swz = (CUtensorMapSwizzle)internal_g3_opt(0);
+    const CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS && getenv("CTCB200_DEBUG"))
+        fprintf(stderr, "ctcb200: cuTensorMapEncodeTiled -> %d (base %p rows %lld inner %lld pitch %lld box_rows %d mn %d)\n",
+                (int)r, (const void *)base, (long long)rows, (long long)inner, (long long)pitch, box_rows, (int)mn);
+    return r == CUDA_SUCCESS ? 0 : CTCB200_ERR_SHAPE;
+}
+
+uint64_t mn_desc_bits() {
+    const int lbo = internal_g3_opt(1), sbo = internal_g3_opt(2), layout = internal_g3_opt(3);
+    return umma_desc_mn_hi(lbo > 0 ? lbo : 4096, sbo > 0 ? sbo : 512, layout > 0 ? layout : 1);
+}
+
+template <bool A_MN, bool B_MN>
+int launch_gemm3(int sms, cudaStream_t s, const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &ga) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm3<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    const int items = ((ga.Mc + HM - 1) / HM) * ((ga.Nc + HN - 1) / HN) * ga.ksplit;
+    k_gemm3<A_MN, B_MN><<<items < sms ? items : sms, G_THREADS, G_SMEM, s>>>(ma, mb, ga);
+    return (int)cudaGetLastError();
 }
 
 struct HeadWs {
@@ -118,7 +164,7 @@ int head_impl(bool want_grad, const float *enc, const float *weight, const float
     }
     if (B == 0) return CTCB200_OK;
     int sms = 0;
-    if ((rc = internal_sm_count(&sms))) return rc;
+    if ((rc = internal_sm_count(&sms)) || (rc = ensure_context())) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     unsigned char *ws = (unsigned char *)workspace;
     const int64_t tnumel = targets_stride ? (int64_t)B * targets_stride : targets_numel;
@@ -164,9 +210,72 @@ int head_impl(bool want_grad, const float *enc, const float *weight, const float
                                             : launch_head<1, true>(sms, s, mA_hi, mA_lo, mB_hi, mB_lo, a);
 }
 
+size_t param_grads_ws(int V, int K, int *ksplit) {
+    *ksplit = 2;                                            // 34 class tiles x 2 column tiles x 2 slices = 136 work items
+    return align_up((size_t)(*ksplit) * V * K * 4);
+}
+
 }  // namespace
 
 extern "C" {
+
+int ctcb200_head_param_grads_workspace_bytes(int V, int K, size_t *out_bytes) {
+    if (!out_bytes) return CTCB200_ERR_NULL;
+    if (V < 2 || K < HK || (K % HK) != 0) return CTCB200_ERR_SHAPE;
+    int ks;
+    *out_bytes = param_grads_ws(V, K, &ks);
+    return CTCB200_OK;
+}
+
+int ctcb200_head_param_grads(const float *dlogits, int64_t dlogits_pitch, const float *enc, const float *weight, int B,
+                             int T, int V, int K, float *d_enc, float *d_weight, void *workspace, size_t workspace_bytes,
+                             ctcb200_stream_t stream) {
+    if (!dlogits || !enc || !weight || (!d_enc && !d_weight)) return CTCB200_ERR_NULL;
+    if (B < 0 || T < 1 || V < 2 || K < HK || (K % HK) != 0 || (long long)B * T > 0x7fffff00LL) return CTCB200_ERR_SHAPE;
+    if (dlogits_pitch < V || (dlogits_pitch & 3)) return CTCB200_ERR_SHAPE;
+    if (((uintptr_t)dlogits & 15) || ((uintptr_t)enc & 15) || ((uintptr_t)weight & 15) || ((uintptr_t)d_enc & 15) ||
+        ((uintptr_t)d_weight & 15) || ((uintptr_t)workspace & 255))
+        return CTCB200_ERR_ALIGN;
+    int ksplit;
+    const size_t need = d_weight ? param_grads_ws(V, K, &ksplit) : 0;
+    if (d_weight && (!workspace || workspace_bytes < need)) return CTCB200_ERR_WORKSPACE;
+    if (B == 0) return CTCB200_OK;
+    int sms = 0, rc;
+    if ((rc = internal_sm_count(&sms)) || (rc = ensure_context())) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t M = (int64_t)B * T;
+    if (d_enc) {
+        // d enc[M, K] = dlogits[M, V] x W[V, K]:  A = dlogits, K-major (reduction = class index, contiguous);
+        //                                         B = W as [N = K columns, reduction = V rows]: MN-major
+        CUtensorMap ma, mb;
+        if ((rc = make_map_pitched(&ma, dlogits, M, dlogits_pitch, dlogits_pitch, HM, false)) ||
+            (rc = make_map_pitched(&mb, weight, V, K, K, 32, true)))
+            return rc;
+        const GemmArgs ga = {d_enc, K, (int)M, K, (int)dlogits_pitch, 1, 0, mn_desc_bits()};
+        if ((rc = launch_gemm3<false, true>(sms, s, ma, mb, ga))) return rc;
+    }
+    if (d_weight) {
+        // d W[V, K] = dlogits^T x enc:  A = dlogits as [M' = V, reduction = M rows]: MN-major;
+        //                               B = enc as [N = K, reduction = M rows]: MN-major; reduction split in `ksplit` slices
+        CUtensorMap ma, mb;
+        if ((rc = make_map_pitched(&ma, dlogits, M, dlogits_pitch, dlogits_pitch, 32, true)) ||
+            (rc = make_map_pitched(&mb, enc, M, K, K, 32, true)))
+            return rc;
+        int ks = ksplit;
+        const int n_kc = (int)((M + HK - 1) / HK);
+        if (ks > n_kc) ks = 1;
+        float *part = (float *)workspace;
+        const GemmArgs ga = {ks > 1 ? part : d_weight, K, V, K, (int)M, ks, (int64_t)V * K, mn_desc_bits()};
+        if ((rc = launch_gemm3<true, true>(sms, s, ma, mb, ga))) return rc;
+        if (ks > 1) {
+            const size_t n4 = (size_t)V * K / 4;
+            k_sum_partials<<<sms * 2, 256, 0, s>>>(part, d_weight, n4, ks, n4);
+            if ((rc = (int)cudaGetLastError())) return rc;
+        }
+    }
+    return CTCB200_OK;
+}
+
 
 int ctcb200_head_workspace_bytes(int B, int T, int V, int K, int Umax, int precision, size_t *out_bytes) {
     if (!out_bytes) return CTCB200_ERR_NULL;

@@ -103,6 +103,10 @@ __device__ __forceinline__ void stg_f32_hint(float *p, float v, uint64_t policy)
 __device__ __forceinline__ void fence_proxy_async_global() {
     asm volatile("fence.proxy.async.global;" ::: "memory");
 }
+// generic-proxy writes to shared memory -> later async-proxy reads of the same bytes (tcgen05.mma operands, bulk copies)
+__device__ __forceinline__ void fence_proxy_async_smem_cta() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -169,7 +169,7 @@ __device__ __forceinline__ void zero_span(float *p, size_t n, int tid) {   // CT
     float4 *q = (float4 *)(p + h);
     const size_t n4 = (n - h) >> 2;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (size_t i = tid; i < n4; i += NT) q[i] = z;
+    for (size_t i = tid; i < n4; i += NT) stg_v4_hint(q + i, z, kEvictFirst);   // streamed once, like the gradient rows
     const size_t done = h + (n4 << 2);
     if (done + tid < n) p[done + tid] = 0.f;
 }

@@ -25,6 +25,9 @@ from . import _lib
 from .ctc import _CFG, _RED, _as_i64_cuda, _validate_host
 
 _PREC = {"3xtf32": 0, "tf32": 1}
+# how d enc / d W are formed from the gradient buffer: "tcgen05" = this repo's 3xTF32 tensor-core GEMM (k_gemm3),
+# "torch" = torch.matmul (cuBLAS fp32 SIMT GEMMs, what the nn.Linear backward would run)
+_CFG_HEAD = {"param_grads": "tcgen05"}
 
 
 class _CTCHeadLossFn(torch.autograd.Function):
@@ -92,19 +95,40 @@ class _CTCHeadLossFn(torch.autograd.Function):
         dl, x, w = ctx.saved_tensors
         B, T, K, V, red, has_bias = ctx.meta
         go = grad_out.to(torch.float32)
-        d = dl[:, :V]                                        # [B*T, V] view of the pitched buffer
-        if red == 0:                                         # per-utterance upstream gradient
-            d = (dl.view(B, T, -1) * go.view(B, 1, 1)).view(B * T, -1)[:, :V]
+        if red == 0:                                         # per-utterance upstream gradient: a scaled copy, same pitch
+            dl = (dl.view(B, T, -1) * go.view(B, 1, 1)).view(B * T, -1)
             go = None
+        d = dl[:, :V]                                        # [B*T, V] view of the pitched buffer
         g_enc = g_w = g_b = None
-        if ctx.needs_input_grad[0]:
-            g_enc = torch.matmul(d, w).view(B, T, K)
+        if _CFG_HEAD["param_grads"] == "tcgen05" and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+            # the two parameter-gradient GEMMs on the tensor cores with fp32-grade accuracy (k_gemm3: 3xTF32, operands
+            # split inside the shared-memory ring, MN-major operand tiles -- no transposed copy of the gradient)
+            L = _lib.lib()
+            dev = dl.device
+            if ctx.needs_input_grad[0]:
+                g_enc = torch.empty(B, T, K, dtype=torch.float32, device=dev)
+            if ctx.needs_input_grad[1]:
+                g_w = torch.empty(V, K, dtype=torch.float32, device=dev)
+            wsb = _lib.head_param_grads_workspace_bytes(V, K)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                st = torch.cuda.current_stream().cuda_stream
+                _lib.check(L.ctcb200_head_param_grads(dl.data_ptr(), dl.shape[1], x.data_ptr(), w.data_ptr(), B, T, V, K,
+                                                      g_enc.data_ptr() if g_enc is not None else None,
+                                                      g_w.data_ptr() if g_w is not None else None, ws.data_ptr(), wsb, st),
+                           "ctcb200_head_param_grads")
             if go is not None:
-                g_enc = g_enc * go
-        if ctx.needs_input_grad[1]:
-            g_w = torch.matmul(d.t(), x.view(B * T, K))
-            if go is not None:
-                g_w = g_w * go
+                g_enc = g_enc * go if g_enc is not None else None
+                g_w = g_w * go if g_w is not None else None
+        else:
+            if ctx.needs_input_grad[0]:
+                g_enc = torch.matmul(d, w).view(B, T, K)
+                if go is not None:
+                    g_enc = g_enc * go
+            if ctx.needs_input_grad[1]:
+                g_w = torch.matmul(d.t(), x.view(B * T, K))
+                if go is not None:
+                    g_w = g_w * go
         if has_bias and ctx.needs_input_grad[2]:
             g_b = d.sum(0)
             if go is not None:

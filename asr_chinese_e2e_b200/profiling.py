@@ -1,8 +1,10 @@
 """Per-stage device timing of the two-sweep loss+grad call, for bench.py's roofline line.
 
-One un-chunked ``ctcb200_loss_grad`` call on the current stream, bracketed by CUDA events on that
+``time_stages``: one un-chunked ``ctcb200_loss_grad`` call on the current stream, bracketed by CUDA events on that
 stream; the library's own ``sweep_done`` event (recorded right after the fused sweep kernel) splits the
 call into  [k0_prep + k1_lse_gather<FUSED>]  and  [k2_lattice + k3p_patch].
+``time_sweep_kernel``: the dominant kernel by itself -- the stage-split entry point launches k0_prep (stage 8) and the
+fused sweep (stage 16) separately with an event in between, so the timed interval holds k1_lse_gather<FUSED> alone.
 """
 from __future__ import annotations
 
@@ -46,3 +48,37 @@ def time_stages(logits, targets, input_lengths, target_lengths, blank=0, reducti
         _lib.check(L.ctcb200_read_lattice_stats(ws.data_ptr(), stats, st.cuda_stream), "ctcb200_read_lattice_stats")
         out["lattice_stats"] = [int(stats[0]), int(stats[1])]
     return out
+
+
+def time_sweep_kernel(logits, targets, input_lengths, target_lengths, blank=0, reduction="mean", zero_infinity=False,
+                      iters=10, warmup=3):
+    """Average duration (ms) of the fused sweep kernel alone, CUDA events on the launching stream."""
+    x, tg, stride, il, tl, B, T, V, umax = _prepare(logits.detach(), targets, input_lengths, target_lengths, blank, None)
+    L = _lib.lib()
+    ws_bytes = _lib.workspace_bytes(B, T, V, umax)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    nll = torch.empty(B, device=x.device)
+    sums = torch.zeros(4, device=x.device)
+    grad = torch.empty_like(x)
+    out = []
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream()
+
+        def call(stages):
+            _lib.check(L.ctcb200_loss_grad_stages(stages, x.data_ptr(), tg.data_ptr(), stride, tg.numel(), il.data_ptr(),
+                                                  tl.data_ptr(), B, T, V, umax, int(blank), int(bool(zero_infinity)),
+                                                  _RED[reduction], 1.0 / max(B, 1), nll.data_ptr(), sums.data_ptr(),
+                                                  grad.data_ptr(), ws.data_ptr(), ws_bytes, st.cuda_stream),
+                       "ctcb200_loss_grad_stages")
+        for i in range(warmup + iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            call(8)
+            e0.record(st)
+            call(16)
+            e1.record(st)
+            call(2 | 4)
+            e1.synchronize()
+            if i >= warmup:
+                out.append(e0.elapsed_time(e1))
+        torch.cuda.synchronize()
+    return sum(out) / len(out)

@@ -147,7 +147,8 @@ int ctcb200_loss_grad(const float *logits, const int64_t *targets, int64_t targe
 /* The same call, one stage at a time, for callers that pipeline utterance chunks over two streams
  * (the lattice is latency-bound and should run under another chunk's sweep):
  * stages is a bit mask of  1 = prep + fused sweep,  2 = lattice,  4 = sparse patch; each stage must
- * be ordered after the previous stage of the same workspace by the caller (events). */
+ * be ordered after the previous stage of the same workspace by the caller (events).  For profiling, 8 = prep alone
+ * and 16 = fused sweep alone split stage 1 in two (bench.py times the dominant kernel by itself this way). */
 int ctcb200_loss_grad_stages(int stages, const float *logits, const int64_t *targets,
                              int64_t targets_stride, int64_t targets_numel, const int64_t *in_len,
                              const int64_t *tgt_len, int B, int T, int V, int Umax, int blank,
@@ -233,6 +234,18 @@ int ctcb200_head_loss_grad(const float *enc, const float *weight, const float *b
                            int B, int T, int V, int K, int Umax, int blank, int flags, int precision, int reduction,
                            float inv_batch, float *nll, float *loss_sums, float *dlogits, int64_t dlogits_pitch,
                            void *workspace, size_t workspace_bytes, ctcb200_stream_t stream);
+
+/* The two parameter-gradient GEMMs of the fused head, on the tensor cores with fp32-grade accuracy (3xTF32: every fp32
+ * operand tile is split into hi + lo tf32 halves inside the shared-memory ring, three tcgen05.mma passes accumulate in
+ * fp32) -- what torch.autograd would run as two fp32 SIMT GEMMs for the nn.Linear it replaces:
+ *   d_enc[B*T, K]   = dlogits[B*T, V] x weight[V, K]          (NULL to skip)
+ *   d_weight[V, K]  = dlogits[B*T, V]^T x enc[B*T, K]         (NULL to skip; needs the workspace: two partial sums)
+ * dlogits is the buffer ctcb200_head_loss_grad wrote (row pitch dlogits_pitch floats, columns >= V zero).
+ * d_bias is the column sum of dlogits (left to the caller).  K % 32 == 0; all pointers 16-byte aligned. */
+int ctcb200_head_param_grads_workspace_bytes(int V, int K, size_t *out_bytes);
+int ctcb200_head_param_grads(const float *dlogits, int64_t dlogits_pitch, const float *enc, const float *weight, int B,
+                             int T, int V, int K, float *d_enc, float *d_weight, void *workspace, size_t workspace_bytes,
+                             ctcb200_stream_t stream);
 
 /* Debug: copies the device status word to *host_status (synchronises `stream`). */
 int ctcb200_read_status(const void *workspace, int *host_status, ctcb200_stream_t stream);

@@ -156,3 +156,63 @@ def test_joint_mixin_with_the_fused_head():
     for k in res[True][1]:
         a, b = res[True][1][k], res[False][1][k]
         assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item() + 1e-8, k
+
+
+@pytest.mark.parametrize("shape", [(1, 128, 32, 32), (2, 64, 40, 32), (3, 100, 300, 64), (2, 333, 700, 128),
+                                   (8, 200, 4234, 512), (64, 400, 1030, 96)])
+def test_param_grad_gemms_are_fp32_grade(shape):
+    """ctcb200_head_param_grads (k_gemm3: 3xTF32 on tcgen05, MN-major operand tiles, accumulators drained every 256
+    reduction elements) against float64 matmuls: the error must stay within 4x of cuBLAS's fp32 SIMT GEMM (plus a floor of
+    2e-6 of the result's scale) -- ragged tile edges in every dimension, and a 25 600-long reduction for d W."""
+    from asr_chinese_e2e_b200 import _lib
+    B, T, V, K = shape
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(B * 1000 + V)
+    pitch = (V + 3) // 4 * 4
+    dl = torch.zeros(B * T, pitch)
+    dl[:, :V] = torch.randn(B * T, V, generator=g) * 1e-2
+    enc = torch.randn(B * T, K, generator=g)
+    w = torch.randn(V, K, generator=g) / K ** 0.5
+    dl_d, enc_d, w_d = dl.cuda(), enc.cuda(), w.cuda()
+    g_enc = torch.full((B * T, K), 7.0, device="cuda")
+    g_w = torch.full((V, K), 7.0, device="cuda")
+    wsb = _lib.head_param_grads_workspace_bytes(V, K)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for want_enc, want_w in ((True, True), (True, False), (False, True)):
+        g_enc.fill_(7.0)
+        g_w.fill_(7.0)
+        rc = L.ctcb200_head_param_grads(dl_d.data_ptr(), pitch, enc_d.data_ptr(), w_d.data_ptr(), B, T, V, K,
+                                        g_enc.data_ptr() if want_enc else None, g_w.data_ptr() if want_w else None,
+                                        ws.data_ptr(), wsb, st)
+        assert rc == 0, _lib.strerror(rc)
+        torch.cuda.synchronize()
+        ref_enc = dl_d[:, :V].double() @ w_d.double()
+        ref_w = dl_d[:, :V].double().t() @ enc_d.double()
+        if want_enc:
+            err = (g_enc.double() - ref_enc).abs().max().item()
+            lib = ((dl_d[:, :V] @ w_d).double() - ref_enc).abs().max().item()
+            assert err <= 4 * lib + 2e-6 * ref_enc.abs().max().item(), ("d_enc", err, lib)
+        else:
+            assert (g_enc == 7.0).all()
+        if want_w:
+            err = (g_w.double() - ref_w).abs().max().item()
+            lib = ((dl_d[:, :V].t() @ enc_d).double() - ref_w).abs().max().item()
+            assert err <= 4 * lib + 2e-6 * ref_w.abs().max().item(), ("d_weight", err, lib)
+        else:
+            assert (g_w == 7.0).all()
+
+
+def test_param_grad_paths_agree():
+    """param_grads='tcgen05' (default) and 'torch' (cuBLAS fp32) give the same parameter gradients."""
+    from asr_chinese_e2e_b200 import head
+    case = _case(4, 120, 64, 500, 9, 3)
+    res = {}
+    for mode in ("tcgen05", "torch"):
+        head._CFG_HEAD["param_grads"] = mode
+        try:
+            res[mode] = _run(case, "3xtf32")[2]
+        finally:
+            head._CFG_HEAD["param_grads"] = "tcgen05"
+    for a, b in zip(res["tcgen05"], res["torch"]):
+        assert (a - b).abs().max().item() <= 2e-5 * b.abs().max().item() + 1e-9   # cuBLAS fp32 itself is ~3e-6 off
