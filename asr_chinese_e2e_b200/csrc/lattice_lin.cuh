@@ -484,7 +484,26 @@ k2_lattice(const int64_t *__restrict__ targets, int64_t tnumel, const int *__res
     if (b >= B) return;                                          // odd batch: the last CTA has one utterance
     const int Tb = __ldcg(Tb_arr + b), Ub = __ldcg(Ub_arr + b);   // (ld.global.cg: see stream_kernels.cuh, cursor helpers)
 
+    // Structural feasibility: an alignment exists iff T_b >= U_b + (number of adjacent equal labels).  An infeasible
+    // utterance is settled here -- otherwise it would run the linear recursion up to its underflow at the midpoint AND
+    // the log-space recursion after it, and the launch lasts as long as its slowest utterance (C4: 8 of 64).
+    bool infeasible = false;
     if (Tb > 0) {
+        const int64_t toff = __ldcg(toff_arr + b);
+        int rep = 0;
+        for (int j = 1 + lane; j < Ub; j += 32) {
+            const int64_t i1 = toff + j;
+            rep += (i1 < tnumel ? (int)targets[i1] : 0) == (i1 - 1 < tnumel ? (int)targets[i1 - 1] : 0);
+        }
+        rep = __reduce_add_sync(0xffffffffu, rep);
+        infeasible = Tb < Ub + rep;
+    }
+    if (infeasible) {
+        if (dir == 0 && lane == 0) {
+            nll[b] = zero_inf ? 0.f : __int_as_float(0x7f800000);
+            flags[b] = 1;
+        }
+    } else if (Tb > 0) {
         const int64_t toff = __ldcg(toff_arr + b);
         // fast path: linear-domain recursion; utterances outside its range (slow[b], set by the sweep) or whose
         // likelihood underflows (which includes the infeasible ones) run the log-space recursion

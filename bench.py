@@ -610,11 +610,14 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e["ms_per_step"] = float(t.item())
             e["value"] = world * B_ / (e["ms_per_step"] / 1e3)
-            e["h2d_bytes_per_step"] *= world; e["d2h_bytes_per_step"] *= world
+            nb = torch.tensor([e["h2d_bytes_per_step"], e["d2h_bytes_per_step"]], device=dev, dtype=torch.float64)
+            dist.all_reduce(nb, op=dist.ReduceOp.SUM)              # each rank copies its own valid frames
+            e["h2d_bytes_per_step"], e["d2h_bytes_per_step"] = int(nb[0].item()), int(nb[1].item())
         line["e2e"] = e
         if world == 1:
             # the training-shaped variant: the gradient's consumer is the next GPU kernel, only the loss goes back
             line["e2e_grad_on_device"] = run_e2e(torch, c, args, dev, grad_to_host=False)
+            line["e2e_all_frames"] = run_e2e(torch, c, args, dev, valid_frames_only=False)
 
     if not args.no_configs:
         cfgs = {}
@@ -665,10 +668,11 @@ def run_torch_cuda(torch, c, dev):
             "what": f"torch {torch.__version__} CUDA F.log_softmax + F.ctc_loss(mean) + backward, same inputs, 10 steps"}
 
 
-def run_e2e(torch, c, args, dev, grad_to_host=True):
+def run_e2e(torch, c, args, dev, grad_to_host=True, valid_frames_only=True):
     """Host-buffer API: pinned logits -> device, kernels, gradient + nll -> pinned host, every step."""
     from asr_chinese_e2e_b200.host_pipeline import HostCTCPipeline
-    pipe = HostCTCPipeline(B_, T_, V_, U_, chunk=32, device=dev, grad_to_host=grad_to_host)
+    pipe = HostCTCPipeline(B_, T_, V_, U_, chunk=16, device=dev, grad_to_host=grad_to_host,
+                           valid_frames_only=valid_frames_only)
     h_x = c["logits"].pin_memory()
     h_tg, h_il, h_tl = c["targets"].pin_memory(), c["input_lengths"].pin_memory(), c["target_lengths"].pin_memory()
     h_g = torch.empty(B_, T_, V_, pin_memory=True)
@@ -690,8 +694,11 @@ def run_e2e(torch, c, args, dev, grad_to_host=True):
             "d2h_bytes_per_step": d2h, "ms_per_step": ms, "steps": k, "loss": loss,
             "api": "asr_chinese_e2e_b200.host_pipeline.HostCTCPipeline (pinned host logits in; "
                    + ("grad[B,T,V] + " if grad_to_host else "gradient left on the device, ")
-                   + "nll[B] back to pinned host; 3-stream chunked pipeline, chunk=32 utterances)",
-            "gpu_launches_per_step": launches}
+                   + "nll[B] back to pinned host; 3-stream chunked pipeline, chunk=16 utterances; "
+                   + ("only the valid frames (t < input_lengths[b]) cross PCIe, the padded gradient rows are zeroed "
+                      "on the host inside the timed call" if valid_frames_only else "whole [B,T,V] tensors cross PCIe")
+                   + ")",
+            "valid_frames_only": bool(valid_frames_only), "gpu_launches_per_step": launches}
 
 
 if __name__ == "__main__":

@@ -47,6 +47,37 @@ def test_host_pipeline_matches_oracle():
     assert (grad - rg).abs().max().item() <= 1e-4
 
 
+def test_host_pipeline_valid_frames_only_is_bit_identical():
+    """valid_frames_only (default) moves only the frames t < input_lengths[b] over PCIe and zeroes the padded rows of
+    the host gradient on the host; zero_copy_logits (default) lets the sweep kernel read the pinned host logits in
+    place.  Every combination gives the same bits as whole tensors through the copy engines, on a dirty host buffer,
+    with full-length runs, ragged and zero-length utterances; the byte counters reflect what crossed the bus."""
+    from asr_chinese_e2e_b200.host_pipeline import HostCTCPipeline
+    B, T, V, U = 10, 40, 133, 7
+    outs = {}
+    for seed, lens in ((1, [40, 40, 40, 17, 0, 40, 25, 40, 40, 31]), (2, [12, 40, 40, 40, 40, 9, 40, 33, 40, 40])):
+        c = make_case(B, T, V, U, seed, dist="D1")
+        il = torch.tensor(lens)
+        il = torch.where(il > 0, torch.maximum(il, 2 * c["target_lengths"] + 1), il)
+        pin = lambda t: t.contiguous().pin_memory()
+        for vfo, zc in ((True, True), (True, False), (False, True), (False, False)):
+            pipe = HostCTCPipeline(B, T, V, U, chunk=4, zero_infinity=True, valid_frames_only=vfo, zero_copy_logits=zc)
+            h_g = torch.full((B, T, V), float("nan")).pin_memory()
+            h_n = torch.empty(B).pin_memory()
+            pipe(pin(c["logits"]), pin(c["targets"]), pin(il), pin(c["target_lengths"]), h_g, h_n)
+            outs[(seed, vfo, zc)] = (h_g.clone(), h_n.clone())
+            valid = int(il.sum())
+            small = B * U * 8 + 2 * B * 8                       # targets + the two length vectors
+            assert pipe.d2h_bytes == (valid if vfo else B * T) * V * 4 + B * 4
+            assert pipe.h2d_bytes == (valid if (vfo or zc) else B * T) * V * 4 + small   # the sweep reads valid frames only
+        ref = outs[(seed, False, False)]                        # whole tensors through the copy engines
+        for key, got in outs.items():
+            if key[0] == seed:
+                assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]), key
+        tmask = torch.arange(T)[None, :] < il[:, None]
+        assert (ref[0][~tmask] == 0).all()
+
+
 def test_stage_split_abi_equals_single_call():
     from asr_chinese_e2e_b200 import _lib
     L = _lib.lib()
