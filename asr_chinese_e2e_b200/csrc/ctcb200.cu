@@ -30,7 +30,7 @@ enum OptId {
     OPT_PDL, OPT_LATTICE_LOG, OPT_LIN_THR, OPT_K1F_NT, OPT_K1F_NST, OPT_K1F_CPS, OPT_K1_NT, OPT_K1_NST, OPT_K1_CPS,
     OPT_K3_NT, OPT_K3_NST, OPT_K3_CPS, OPT_CE_NST, OPT_CE_CPS, OPT_K3P_CPS, OPT_OCC_SKIP_BITS,
     OPT_ZERO_IN_LATTICE, OPT_ZERO_CPS, OPT_SKIP_LATTICE, OPT_LABEL_KEEP_L2, OPT_SWEEP_DIRECT, OPT_K1D_CPS,
-    OPT_G3_SWZ, OPT_G3_LBO, OPT_G3_SBO, OPT_G3_LAYOUT, OPT_COUNT
+    OPT_G3_SWZ, OPT_G3_LBO, OPT_G3_SBO, OPT_G3_LAYOUT, OPT_G3_RNA_SPLIT, OPT_SCRATCH_POLICY, OPT_COUNT
 };
 struct Opt { const char *name, *env; int value; };
 Opt g_opt[OPT_COUNT] = {
@@ -62,6 +62,11 @@ Opt g_opt[OPT_COUNT] = {
     // type (0 = the kernel's defaults: SWIZZLE_128B_ATOM_32B boxes, LBO 4096, SBO 512, layout SWIZZLE_128B_BASE32B)
     {"g3_swz", "CTCB200_G3_SWZ", 0}, {"g3_lbo", "CTCB200_G3_LBO", 0}, {"g3_sbo", "CTCB200_G3_SBO", 0},
     {"g3_layout", "CTCB200_G3_LAYOUT", 0},
+    // k_gemm3: 1 = round-to-nearest hi/lo split written by the converter warps before any MMA of the stage (the first
+    // version); 0 = truncation split, the raw tile is the hi half and a third of the MMAs runs under the conversion
+    {"g3_rna_split", "CTCB200_G3_RNA_SPLIT", 0},
+    // L2 policy of the scratch arrays between the kernels of a step: 0 evict_last, 1 evict_normal, 2 evict_first
+    {"scratch_policy", "CTCB200_SCRATCH_POLICY", 0},
 };
 const bool g_opt_loaded = [] {
     for (Opt &o : g_opt) {
@@ -72,6 +77,20 @@ const bool g_opt_loaded = [] {
 }();
 inline int opt(OptId id) { return g_opt[id].value; }
 inline int opt_or(OptId id, int dflt) { return g_opt[id].value > 0 ? g_opt[id].value : dflt; }
+
+// push the scratch-array L2 policy to the device when the option changed (stream-ordered with the launches after it)
+int apply_scratch_policy(cudaStream_t s) {
+    static int applied = 0;
+    const int want = opt(OPT_SCRATCH_POLICY);
+    if (want == applied) return 0;
+    const uint64_t pol = want == 1 ? kEvictNormal : (want == 2 ? kEvictFirst : kEvictLast);
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_scratch_policy, &pol, sizeof(pol), 0, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaStreamSynchronize(s);                               // `pol` is a stack variable
+    if (e != cudaSuccess) return (int)e;
+    applied = want;
+    return 0;
+}
 
 struct DevInfo {
     int sms;
@@ -279,6 +298,7 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     DevInfo dev;
     if ((rc = device_info(&dev))) return rc;
     cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = apply_scratch_policy(s))) return rc;
     unsigned char *ws = (unsigned char *)workspace;
     int *hdr = (int *)(ws + w.hdr);
     int *Tb = (int *)(ws + w.Tb), *Ub = (int *)(ws + w.Ub), *flags = (int *)(ws + w.flags);

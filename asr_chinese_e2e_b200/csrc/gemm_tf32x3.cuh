@@ -61,7 +61,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32_major(int M, int N, bool 
 
 // A_MN / B_MN: operand is MN-major (tensor map: inner dimension = the operand's M / N index, box 32 x 32);
 // otherwise K-major (inner dimension = reduction index, box 32 x 128 for A / 32 x 256 for B).
-template <bool A_MN, bool B_MN>
+// TRUNC: how x = hi + lo is formed.  false: hi = rna_tf32(x) written in place, lo = x - hi (|lo| <= 2^-11 |x|); every
+// MMA of a stage waits for the converters.  true (default): the tensor core ignores the 13 low mantissa bits of a
+// tf32 operand, so the RAW tile the TMA delivered already IS hi = trunc_tf32(x); the converters only write
+// lo = x - trunc_tf32(x) (exact, |lo| < 2^-10 |x|) and the hi*hi third of the stage's MMAs is issued the moment the
+// tile lands, under the conversion -- the stage's critical path loses the converter latency.
+template <bool A_MN, bool B_MN, bool TRUNC>
 __global__ void __launch_bounds__(G_THREADS, 1)
 k_gemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs a) {
     extern __shared__ unsigned char smem_raw[];
@@ -142,21 +147,29 @@ k_gemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                     tc_fence_after();
                     const uint32_t tacc = tmem_base + (uint32_t)(acc * HN);
                     for (int kc = sg0; kc < sg1; ++kc) {
-                        mbar_wait_bounded(conv(s), ph);                    // landed AND split into hi / lo
-                        tc_fence_after();
                         const uint32_t st = sbase + s * G_STAGE;
                         const uint32_t a_hi = st, a_lo = st + H_A_BYTES, b_hi = st + 2 * H_A_BYTES, b_lo = b_hi + H_B_BYTES;
+                        // 8 reduction indices per instruction: 32 bytes along a K-major row, 8 rows (1024 B) of an MN-major tile
+                        auto adesc = [&](uint32_t base, int k) {
+                            return A_MN ? umma_desc_mn(base + k * 1024, a.mn_desc) : umma_desc_k128(base + k * 32);
+                        };
+                        auto bdesc = [&](uint32_t base, int k) {
+                            return B_MN ? umma_desc_mn(base + k * 1024, a.mn_desc) : umma_desc_k128(base + k * 32);
+                        };
+                        if (TRUNC) {
+                            mbar_wait_bounded(full(s), ph);                // landed: the raw tiles are the hi halves
+                            tc_fence_after();
+#pragma unroll
+                            for (int k = 0; k < HK / 8; ++k)
+                                umma_tf32(tacc, adesc(a_hi, k), bdesc(b_hi, k), idesc, (kc > sg0 || k > 0) ? 1u : 0u);
+                        }
+                        mbar_wait_bounded(conv(s), ph);                    // the lo halves (RNA split: hi as well) are written
+                        tc_fence_after();
 #pragma unroll
                         for (int k = 0; k < HK / 8; ++k) {
-                            // 8 reduction indices per instruction: 32 bytes along a K-major row, 8 rows (1024 B) of an MN-major tile
-                            const uint32_t ka = A_MN ? k * 1024 : k * 32, kb = B_MN ? k * 1024 : k * 32;
-                            const uint64_t dah = A_MN ? umma_desc_mn(a_hi + ka, a.mn_desc) : umma_desc_k128(a_hi + ka);
-                            const uint64_t dal = A_MN ? umma_desc_mn(a_lo + ka, a.mn_desc) : umma_desc_k128(a_lo + ka);
-                            const uint64_t dbh = B_MN ? umma_desc_mn(b_hi + kb, a.mn_desc) : umma_desc_k128(b_hi + kb);
-                            const uint64_t dbl = B_MN ? umma_desc_mn(b_lo + kb, a.mn_desc) : umma_desc_k128(b_lo + kb);
-                            umma_tf32(tacc, dal, dbh, idesc, (kc > sg0 || k > 0) ? 1u : 0u);
-                            umma_tf32(tacc, dah, dbl, idesc, 1);
-                            umma_tf32(tacc, dah, dbh, idesc, 1);
+                            umma_tf32(tacc, adesc(a_lo, k), bdesc(b_hi, k), idesc, (TRUNC || kc > sg0 || k > 0) ? 1u : 0u);
+                            umma_tf32(tacc, adesc(a_hi, k), bdesc(b_lo, k), idesc, 1);
+                            if (!TRUNC) umma_tf32(tacc, adesc(a_hi, k), bdesc(b_hi, k), idesc, 1);
                         }
                         umma_commit(empty(s));
                         if (++s == G_NSTAGE) { s = 0; ph ^= 1; }
@@ -181,12 +194,20 @@ k_gemm3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
                 auto split = [](float4 *hi, float4 *lo, int i) {
                     const float4 x = hi[i];
                     float4 h, l;
-                    uint32_t u;
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.x)); h.x = __uint_as_float(u); l.x = x.x - h.x;
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.y)); h.y = __uint_as_float(u); l.y = x.y - h.y;
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.z)); h.z = __uint_as_float(u); l.z = x.z - h.z;
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.w)); h.w = __uint_as_float(u); l.w = x.w - h.w;
-                    hi[i] = h; lo[i] = l;
+                    if (TRUNC) {
+                        h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
+                        h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
+                        h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
+                        h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
+                        lo[i] = l;                                        // the raw tile stays as it is
+                    } else {
+                        uint32_t u;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.x)); h.x = __uint_as_float(u); l.x = x.x - h.x;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.y)); h.y = __uint_as_float(u); l.y = x.y - h.y;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.z)); h.z = __uint_as_float(u); l.z = x.z - h.z;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.w)); h.w = __uint_as_float(u); l.w = x.w - h.w;
+                        hi[i] = h; lo[i] = l;
+                    }
                 };
 #pragma unroll 4
                 for (int i = ct; i < (int)(H_A_BYTES / 16); i += 64) split(A4, A4 + H_A_BYTES / 16, i);

@@ -86,13 +86,18 @@ uint64_t mn_desc_bits() {
     return umma_desc_mn_hi(lbo > 0 ? lbo : 4096, sbo > 0 ? sbo : 512, layout > 0 ? layout : 1);
 }
 
-template <bool A_MN, bool B_MN>
-int launch_gemm3(int sms, cudaStream_t s, const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &ga) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm3<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+template <bool A_MN, bool B_MN, bool TRUNC>
+int launch_gemm3_t(int sms, cudaStream_t s, const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &ga) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm3<A_MN, B_MN, TRUNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
     if (e != cudaSuccess) return (int)e;
     const int items = ((ga.Mc + HM - 1) / HM) * ((ga.Nc + HN - 1) / HN) * ga.ksplit;
-    k_gemm3<A_MN, B_MN><<<items < sms ? items : sms, G_THREADS, G_SMEM, s>>>(ma, mb, ga);
+    k_gemm3<A_MN, B_MN, TRUNC><<<items < sms ? items : sms, G_THREADS, G_SMEM, s>>>(ma, mb, ga);
     return (int)cudaGetLastError();
+}
+template <bool A_MN, bool B_MN>
+int launch_gemm3(int sms, cudaStream_t s, const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &ga) {
+    return internal_g3_opt(4) ? launch_gemm3_t<A_MN, B_MN, false>(sms, s, ma, mb, ga)      // option g3_rna_split
+                              : launch_gemm3_t<A_MN, B_MN, true>(sms, s, ma, mb, ga);
 }
 
 struct HeadWs {

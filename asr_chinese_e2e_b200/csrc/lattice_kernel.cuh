@@ -96,11 +96,11 @@ __device__ __forceinline__ void lds_vec(float (&d)[N], uint32_t a) {
 template <int N>
 __device__ __forceinline__ void stg_vec(float *p, const float (&d)[N]) {
     if (N == 2) {
-        stg_v2_hint((float2 *)p, make_float2(d[0], d[1]), kEvictLast);
+        stg_v2_hint((float2 *)p, make_float2(d[0], d[1]), kScratch);
     } else {
 #pragma unroll
         for (int k = 0; k < N / 4; ++k)
-            stg_v4_hint((float4 *)p + k, make_float4(d[4 * k], d[4 * k + 1], d[4 * k + 2], d[4 * k + 3]), kEvictLast);
+            stg_v4_hint((float4 *)p + k, make_float4(d[4 * k], d[4 * k + 1], d[4 * k + 2], d[4 * k + 3]), kScratch);
     }
 }
 
@@ -250,8 +250,8 @@ __device__ __forceinline__ void lattice_dir(uint32_t ring, uint32_t bar0, uint32
         const int stg = n % NSTG;
         const uint32_t dst = ring + stg * C::STAGE, bar = bar0 + 8 * stg;
         mbar_expect_tx(bar, rows * C::LP_ROW + (ph2 ? rows * C::AB_ROW : 0));
-        tma_load_1d_hint(dst, lp_base + (size_t)t0 * Lp, rows * C::LP_ROW, bar, kEvictLast);
-        if (ph2) tma_load_1d_hint(dst + TT * C::LP_ROW, ab_base + (size_t)t0 * Sp, rows * C::AB_ROW, bar, kEvictLast);
+        tma_load_1d_hint(dst, lp_base + (size_t)t0 * Lp, rows * C::LP_ROW, bar, kScratch);
+        if (ph2) tma_load_1d_hint(dst + TT * C::LP_ROW, ab_base + (size_t)t0 * Sp, rows * C::AB_ROW, bar, kScratch);
     };
     __syncwarp();
 
@@ -389,7 +389,7 @@ __device__ __forceinline__ void lattice_dir(uint32_t ring, uint32_t bar0, uint32
             for (int r = 0; r < TT; ++r) if (lane == r) mine = gbl[r];
             if (lane < TT) {                                     // lane r writes the header of the r-th processed row
                 const int rr = DIR ? (TT - 1 - lane) : lane;
-                stg_v2_hint((float2 *)(gam_base + (size_t)(t0 + rr) * Lp), make_float2(mine, lds_f32(tile + rr * C::LP_ROW + 4)), kEvictLast);
+                stg_v2_hint((float2 *)(gam_base + (size_t)(t0 + rr) * Lp), make_float2(mine, lds_f32(tile + rr * C::LP_ROW + 4)), kScratch);
             }
         } else {
             // ragged stage, or the stage that holds the midpoint
@@ -400,7 +400,7 @@ __device__ __forceinline__ void lattice_dir(uint32_t ring, uint32_t bar0, uint32
                 if (!GRAD || infeasible) break;
                 gb = warp_sum(gb);
                 if (lane == 0)
-                    stg_v2_hint((float2 *)(gam_base + (size_t)(t0 + rr) * Lp), make_float2(gb, lds_f32(tile + rr * C::LP_ROW + 4)), kEvictLast);
+                    stg_v2_hint((float2 *)(gam_base + (size_t)(t0 + rr) * Lp), make_float2(gb, lds_f32(tile + rr * C::LP_ROW + 4)), kScratch);
             }
         }
         if (!GRAD || infeasible) break;

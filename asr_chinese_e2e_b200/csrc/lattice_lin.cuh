@@ -161,13 +161,13 @@ template <int N>
 __device__ __forceinline__ void stg_vec_if(int pred, float *p, const float (&d)[N]) {
     if (N == 2) {
         asm volatile("{\n .reg .pred q;\n setp.ne.s32 q, %4, 0;\n @q st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;\n}"
-                     ::"l"(p), "f"(d[0]), "f"(d[1]), "l"(kEvictLast), "r"(pred) : "memory");
+                     ::"l"(p), "f"(d[0]), "f"(d[1]), "l"(kScratch), "r"(pred) : "memory");
     } else {
 #pragma unroll
         for (int k = 0; k < N / 4; ++k)
             asm volatile("{\n .reg .pred q;\n setp.ne.s32 q, %6, 0;\n @q st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;\n}"
                          ::"l"(p + 4 * k), "f"(d[4 * k]), "f"(d[4 * k + 1]), "f"(d[4 * k + 2]), "f"(d[4 * k + 3]),
-                         "l"(kEvictLast), "r"(pred) : "memory");
+                         "l"(kScratch), "r"(pred) : "memory");
     }
 }
 
@@ -274,14 +274,14 @@ __device__ __forceinline__ bool lattice_lin_dir(uint32_t ring, uint32_t bar0, ui
         const int stg = n % NSTG;
         const uint32_t dst = ring + stg * C::STAGE, bar = bar0 + 8 * stg;
         mbar_expect_tx(bar, rows * C::LP_ROW + (ph2 ? C::EXPS + rows * RS : 0));
-        tma_load_1d_hint(dst, lp_base + (size_t)t0 * Lp, rows * C::LP_ROW, bar, kEvictLast);
-        if (ph2) tma_load_1d_hint(dst + TT * C::LP_ROW, ab_utt + (size_t)q * BLK, C::EXPS + rows * RS, bar, kEvictLast);
+        tma_load_1d_hint(dst, lp_base + (size_t)t0 * Lp, rows * C::LP_ROW, bar, kScratch);
+        if (ph2) tma_load_1d_hint(dst + TT * C::LP_ROW, ab_utt + (size_t)q * BLK, C::EXPS + rows * RS, bar, kScratch);
     };
     const int act = lane < nact;
     const uint32_t RSd = RS / 8;                                 // row stride in doubles
     auto store_row = [&](double *row) {                          // row: this lane's part of the stored row
 #pragma unroll
-        for (int k = 0; k < NS / 2; ++k) stg_v2f64_hint_if(act, row + 2 * k, L.sum[2 * k], L.sum[2 * k + 1], kEvictLast);
+        for (int k = 0; k < NS / 2; ++k) stg_v2f64_hint_if(act, row + 2 * k, L.sum[2 * k], L.sum[2 * k + 1], kScratch);
     };
 
     // ================= phase 1: recursion + store =================
@@ -431,7 +431,7 @@ __device__ __forceinline__ bool lattice_lin_dir(uint32_t ring, uint32_t bar0, ui
             for (int r = 0; r < TT; ++r) if (lane == r) mine = gbl[r];
             if (lane < TT) {
                 const int rr = DIR ? (TT - 1 - lane) : lane;
-                stg_v2_hint((float2 *)(gam_base + (size_t)(t0 + rr) * Lp), make_float2(mine, lds_f32(tile + rr * C::LP_ROW + 4)), kEvictLast);
+                stg_v2_hint((float2 *)(gam_base + (size_t)(t0 + rr) * Lp), make_float2(mine, lds_f32(tile + rr * C::LP_ROW + 4)), kScratch);
             }
         } else {
 #pragma unroll 1
@@ -443,7 +443,7 @@ __device__ __forceinline__ bool lattice_lin_dir(uint32_t ring, uint32_t bar0, ui
                 if (!GRAD || failed) break;
                 gb = warp_sum(gb);
                 if (lane == 0)
-                    stg_v2_hint((float2 *)(gam_base + (size_t)(t0 + rr) * Lp), make_float2(gb, lds_f32(tile + rr * C::LP_ROW + 4)), kEvictLast);
+                    stg_v2_hint((float2 *)(gam_base + (size_t)(t0 + rr) * Lp), make_float2(gb, lds_f32(tile + rr * C::LP_ROW + 4)), kScratch);
             }
         }
         if (!GRAD || failed) break;

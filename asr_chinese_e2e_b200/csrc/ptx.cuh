@@ -70,6 +70,12 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint3
 // per-frame arrays (lp_lab, gam, stored alpha/beta halves) the lattice kernel re-reads -> evict_last.
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
+// L2 policy of the per-frame scratch arrays (lp_lab, gam, the stored lattice halves): written by one kernel and
+// re-read by the next.  A __constant__ so that the `scratch_policy` option can switch it (ctcb200.cu); per
+// translation unit, only ctcb200.cu's copy is ever changed or used.
+static __constant__ uint64_t c_scratch_policy = kEvictLast;
+#define kScratch c_scratch_policy
 
 __device__ __forceinline__ void tma_load_1d_hint(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar,
                                                  uint64_t policy) {

@@ -460,7 +460,7 @@ k1_lse_gather(const float *__restrict__ logits, const int64_t *__restrict__ targ
                 } else {
                     o = cg[kk] == -2 ? lse2 : (cg[kk] == -3 ? 0.f : kNeg);
                 }
-                stg_f32_hint(frame + k, o, kEvictLast);           // re-read by the lattice kernel
+                stg_f32_hint(frame + k, o, kScratch);             // re-read by the lattice kernel
             }
         }
         if (FUSED) {

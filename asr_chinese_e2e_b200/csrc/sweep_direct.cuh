@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(128, (MAXC <= 17 ? 4 : 2)) k1d_sweep(const K1d
                     } else {
                         o = c == -2 ? lse2 : (c == -3 ? 0.f : kNeg);
                     }
-                    stg_f32_hint(a.lp_lab + ((size_t)b * T + t0 + r) * Lp + q, o, kEvictLast);   // re-read by the lattice
+                    stg_f32_hint(a.lp_lab + ((size_t)b * T + t0 + r) * Lp + q, o, kScratch);   // re-read by the lattice
                 }
             }
         }

@@ -62,7 +62,14 @@ VARIANTS = [{}, {"CTCB200_G3_SBO": "1024"}, {"CTCB200_G3_SWZ": "3", "CTCB200_G3_
             {"CTCB200_G3_SWZ": "3"}, {"CTCB200_G3_LAYOUT": "2"}]
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "variants":
+    if len(sys.argv) > 1 and sys.argv[1] == "split":
+        for v in ({}, {"CTCB200_G3_RNA_SPLIT": "1"}):
+            for cfg in ("3", "5"):
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), cfg], capture_output=True, text=True, timeout=300,
+                                   env={**os.environ, **v})
+                tail = [l for l in r.stdout.splitlines() if l.startswith("GEMMCHECK")]
+                print(v, f"rc={r.returncode}", tail[0][:520] if tail else (r.stdout[-300:] + r.stderr[-800:]), flush=True)
+    elif len(sys.argv) > 1 and sys.argv[1] == "variants":
         for v in VARIANTS:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "3"], capture_output=True, text=True, timeout=300,
                                env={**os.environ, **v})
