@@ -30,7 +30,7 @@ enum OptId {
     OPT_PDL, OPT_LATTICE_LOG, OPT_LIN_THR, OPT_K1F_NT, OPT_K1F_NST, OPT_K1F_CPS, OPT_K1_NT, OPT_K1_NST, OPT_K1_CPS,
     OPT_K3_NT, OPT_K3_NST, OPT_K3_CPS, OPT_CE_NST, OPT_CE_CPS, OPT_K3P_CPS, OPT_OCC_SKIP_BITS,
     OPT_ZERO_IN_LATTICE, OPT_ZERO_CPS, OPT_SKIP_LATTICE, OPT_LABEL_KEEP_L2, OPT_SWEEP_DIRECT, OPT_K1D_CPS,
-    OPT_G3_SWZ, OPT_G3_LBO, OPT_G3_SBO, OPT_G3_LAYOUT, OPT_G3_RNA_SPLIT, OPT_SCRATCH_POLICY, OPT_COUNT
+    OPT_G3_SWZ, OPT_G3_LBO, OPT_G3_SBO, OPT_G3_LAYOUT, OPT_G3_RNA_SPLIT, OPT_HEAD_INRING, OPT_SCRATCH_POLICY, OPT_COUNT
 };
 struct Opt { const char *name, *env; int value; };
 Opt g_opt[OPT_COUNT] = {
@@ -65,6 +65,11 @@ Opt g_opt[OPT_COUNT] = {
     // k_gemm3: 1 = round-to-nearest hi/lo split written by the converter warps before any MMA of the stage (the first
     // version); 0 = truncation split, the raw tile is the hi half and a third of the MMAs runs under the conversion
     {"g3_rna_split", "CTCB200_G3_RNA_SPLIT", 0},
+    // k_head 3xTF32: 0 = operands pre-split in HBM by k_split_tf32 (round-to-nearest), 1 = in-ring truncation split as in
+    // k_gemm3 (no pre-pass, no 2 x 4*B*T*K bytes of workspace).  Measured on B200 at the C2 shape: evaluation 2.05-2.12 ms
+    // pre-split vs 2.32-2.42 ms in-ring (the forward pass is tensor-bound and the converters' shared-memory traffic
+    // slows the MMA), training 9.25-9.37 vs 9.36-9.49 ms -> pre-split stays the default
+    {"head_inring", "CTCB200_HEAD_INRING", 0},
     // L2 policy of the scratch arrays between the kernels of a step: 0 evict_last, 1 evict_normal, 2 evict_first
     {"scratch_policy", "CTCB200_SCRATCH_POLICY", 0},
 };

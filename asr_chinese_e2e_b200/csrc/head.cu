@@ -111,7 +111,7 @@ HeadWs head_layout(int B, int T, int V, int K, const Geom &g, int precision) {
     size_t o = h.ctc.total;
     const size_t ne = align_up((size_t)(B > 0 ? B : 1) * T * K * 4), nw = align_up((size_t)V * K * 4);
     h.enc_hi = h.enc_lo = h.w_hi = h.w_lo = 0;
-    if (precision == CTCB200_HEAD_3XTF32) {
+    if (precision == CTCB200_HEAD_3XTF32 && internal_g3_opt(5) == 0) {       // pre-split operands (not with option head_inring)
         h.enc_hi = o; o += ne;
         h.enc_lo = o; o += ne;
         h.w_hi = o;   o += nw;
@@ -135,16 +135,16 @@ int check_head(const float *enc, const float *weight, const void *targets, const
     return 0;
 }
 
-template <int NPASS, bool GRADPASS>
+template <int NPASS, bool GRADPASS, bool INRING = false>
 int launch_head(int sms, cudaStream_t s, const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &b_hi,
                 const CUtensorMap &b_lo, const HeadArgs &args) {
     constexpr size_t smem = HeadCfg<NPASS>::SMEM;
     static_assert(smem <= kSmemBudget, "shared memory budget");
-    cudaError_t e = cudaFuncSetAttribute(k_head<NPASS, GRADPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_head<NPASS, GRADPASS, INRING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int M = args.B * args.T, n_tiles = (M + HM - 1) / HM;
     const int grid = n_tiles < sms ? n_tiles : sms;
-    k_head<NPASS, GRADPASS><<<grid, H_THREADS, smem, s>>>(a_hi, a_lo, b_hi, b_lo, args);
+    k_head<NPASS, GRADPASS, INRING><<<grid, H_THREADS, smem, s>>>(a_hi, a_lo, b_hi, b_lo, args);
     return (int)cudaGetLastError();
 }
 
@@ -177,8 +177,11 @@ int head_impl(bool want_grad, const float *enc, const float *weight, const float
 
     if ((rc = internal_prep(in_len, tgt_len, targets_stride, B, T, Umax, workspace, h.ctc, s))) return rc;
 
+    // 3xTF32: round-to-nearest pre-split in HBM (default) or, option head_inring = 1, the in-ring truncation split
+    const bool presplit = precision == CTCB200_HEAD_3XTF32 && internal_g3_opt(5) == 0;
+    const bool inring = precision == CTCB200_HEAD_3XTF32 && !presplit;
     const float *a_hi = enc, *a_lo = enc, *b_hi = weight, *b_lo = weight;
-    if (precision == CTCB200_HEAD_3XTF32) {
+    if (presplit) {
         float *eh = (float *)(ws + h.enc_hi), *el = (float *)(ws + h.enc_lo), *wh = (float *)(ws + h.w_hi),
               *wl = (float *)(ws + h.w_lo);
         const size_t ne4 = (size_t)B * T * K / 4, nw4 = (size_t)V * K / 4;       // K % 32 == 0
@@ -203,16 +206,18 @@ int head_impl(bool want_grad, const float *enc, const float *weight, const float
     a.B = B; a.T = T; a.V = V; a.K = K; a.Lp = g.Lp; a.blank = blank; a.zero_inf = zero_inf; a.reduction = reduction;
     a.inv_batch = inv_batch; a.lin_thr = internal_lin_thr(g, flags); a.occ_skip = internal_occ_skip();
 
-    rc = precision == CTCB200_HEAD_3XTF32 ? launch_head<3, false>(sms, s, mA_hi, mA_lo, mB_hi, mB_lo, a)
-                                          : launch_head<1, false>(sms, s, mA_hi, mA_lo, mB_hi, mB_lo, a);
+    rc = inring     ? launch_head<3, false, true>(sms, s, mA_hi, mA_lo, mB_hi, mB_lo, a)
+         : presplit ? launch_head<3, false>(sms, s, mA_hi, mA_lo, mB_hi, mB_lo, a)
+                    : launch_head<1, false>(sms, s, mA_hi, mA_lo, mB_hi, mB_lo, a);
     if (rc) return rc;
     const float mean_scale = want_grad ? inv_batch : 1.f / (float)B;
     if ((rc = internal_lattice(want_grad, targets, tnumel, B, T, V, zero_inf, nll, loss_sums, mean_scale, workspace, h.ctc,
                                g, s)))
         return rc;
     if (!want_grad) return CTCB200_OK;
-    return precision == CTCB200_HEAD_3XTF32 ? launch_head<3, true>(sms, s, mA_hi, mA_lo, mB_hi, mB_lo, a)
-                                            : launch_head<1, true>(sms, s, mA_hi, mA_lo, mB_hi, mB_lo, a);
+    return inring     ? launch_head<3, true, true>(sms, s, mA_hi, mA_lo, mB_hi, mB_lo, a)
+           : presplit ? launch_head<3, true>(sms, s, mA_hi, mA_lo, mB_hi, mB_lo, a)
+                      : launch_head<1, true>(sms, s, mA_hi, mA_lo, mB_hi, mB_lo, a);
 }
 
 size_t param_grads_ws(int V, int K, int *ksplit) {

@@ -37,8 +37,8 @@ struct HeadCfg {
     static constexpr uint32_t STAGE = (NPASS == 3 ? 2 : 1) * (H_A_BYTES + H_B_BYTES);
     static constexpr int NSTAGE = NPASS == 3 ? 2 : 4;
     static constexpr uint32_t RING = NSTAGE * STAGE;          // 192 KB
-    static constexpr uint32_t OFF_BARS = RING;                 // full[NSTAGE], empty[NSTAGE], tfull[2], tempty[2]
-    static constexpr uint32_t OFF_TMEM = OFF_BARS + 8 * (2 * NSTAGE + 4);
+    static constexpr uint32_t OFF_BARS = RING;                 // full[NSTAGE], empty[NSTAGE], tfull[2], tempty[2], conv[NSTAGE]
+    static constexpr uint32_t OFF_TMEM = OFF_BARS + 8 * (3 * NSTAGE + 4);
     static constexpr uint32_t OFF_BIAS = OFF_TMEM + 16;        // float[2][HN]
     static constexpr uint32_t SMEM = OFF_BIAS + 2 * HN * 4 + 1024;   // + slack to align the ring to 1024 B
 };
@@ -148,10 +148,19 @@ __device__ __forceinline__ bool head_tile_live(int tile, const int *Tb, int B, i
     return false;
 }
 
-template <int NPASS, bool GRADPASS>
+// INRING (3xTF32 only; option head_inring, off by default -- measured slower, see ctcb200.cu): the operands are NOT pre-split in HBM.  The TMA delivers
+// the raw fp32 tiles of enc / W (tmA_hi / tmB_hi then map the caller's tensors themselves); the tensor core ignores
+// the 13 low mantissa bits of a tf32 operand, so the raw tile IS hi = trunc_tf32(x); warps 2-3 write
+// lo = x - trunc_tf32(x) (exact) into the stage's second tile and the hi*hi third of the stage's MMAs is issued the
+// moment the tile lands, under the conversion (as in k_gemm3, gemm_tf32x3.cuh).  Against the pre-split variant this
+// halves the operand bytes the ring pulls through L2 (the gradient pass re-read 5.0 GB from DRAM for 0.45 GB of
+// operands because the hi/lo tiles fell out of L2 under the gradient stream), and removes the k_split_tf32 pre-pass
+// with its 2 x 4*B*T*K bytes of workspace.
+template <int NPASS, bool GRADPASS, bool INRING = false>
 __global__ void __launch_bounds__(H_THREADS, 1)
 k_head(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
        const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const HeadArgs a) {
+    static_assert(!INRING || NPASS == 3, "the in-ring split is the 3xTF32 product");
     using C = HeadCfg<NPASS>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;           // SWIZZLE_128B atoms need 1024-byte alignment
@@ -161,6 +170,7 @@ k_head(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUten
     auto empty = [&](int s) { return bars + 8 * (C::NSTAGE + s); };
     auto tfull = [&](int i) { return bars + 8 * (2 * C::NSTAGE + i); };
     auto tempty = [&](int i) { return bars + 8 * (2 * C::NSTAGE + 2 + i); };
+    auto conv = [&](int s) { return bars + 8 * (2 * C::NSTAGE + 4 + s); };
     volatile uint32_t *tmem_slot = (volatile uint32_t *)(sgen + C::OFF_TMEM);
     float *sbias = (float *)(sgen + C::OFF_BIAS);
 
@@ -170,10 +180,10 @@ k_head(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUten
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmB_hi);
-        if (NPASS == 3) { prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_lo); }
+        if (NPASS == 3 && !INRING) { prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_lo); }
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); mbar_init(conv(s), 2); }
         for (int i = 0; i < 2; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 4); }
         fence_mbar_init();
     }
@@ -194,9 +204,11 @@ k_head(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUten
                     for (int kc = 0; kc < n_kc; ++kc) {
                         mbar_wait_or_trap(empty(s), ph ^ 1);
                         const uint32_t st = sbase + s * C::STAGE;
-                        mbar_expect_tx(full(s), C::STAGE);
+                        mbar_expect_tx(full(s), INRING ? H_A_BYTES + H_B_BYTES : C::STAGE);
                         tma_load_2d(st, &tmA_hi, kc * HK, row0, full(s));
-                        if (NPASS == 3) {
+                        if (INRING) {
+                            tma_load_2d_hint(st + 2 * H_A_BYTES, &tmB_hi, kc * HK, nt * HN, full(s), kEvictLast);
+                        } else if (NPASS == 3) {
                             tma_load_2d(st + H_A_BYTES, &tmA_lo, kc * HK, row0, full(s));
                             tma_load_2d_hint(st + 2 * H_A_BYTES, &tmB_hi, kc * HK, nt * HN, full(s), kEvictLast);
                             tma_load_2d_hint(st + 2 * H_A_BYTES + H_B_BYTES, &tmB_lo, kc * HK, nt * HN, full(s), kEvictLast);
@@ -226,6 +238,18 @@ k_head(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUten
                         const uint32_t st = sbase + s * C::STAGE;
                         const uint32_t a_hi = st, a_lo = st + H_A_BYTES;
                         const uint32_t b_hi = st + (NPASS == 3 ? 2 : 1) * H_A_BYTES, b_lo = b_hi + H_B_BYTES;
+                        if (INRING) {
+#pragma unroll
+                            for (int k = 0; k < HK / 8; ++k)               // the raw tiles are the hi halves: no wait for warps 2-3
+                                umma_tf32(tacc, umma_desc_k128(a_hi + k * 32), umma_desc_k128(b_hi + k * 32), idesc, (kc | k) != 0);
+                            mbar_wait_or_trap(conv(s), ph);                // the lo halves are written
+                            tc_fence_after();
+#pragma unroll
+                            for (int k = 0; k < HK / 8; ++k) {
+                                umma_tf32(tacc, umma_desc_k128(a_lo + k * 32), umma_desc_k128(b_hi + k * 32), idesc, 1);
+                                umma_tf32(tacc, umma_desc_k128(a_hi + k * 32), umma_desc_k128(b_lo + k * 32), idesc, 1);
+                            }
+                        } else
 #pragma unroll
                         for (int k = 0; k < HK / 8; ++k) {                 // UMMA K = 8 tf32 = 32 bytes inside the 128 B row
                             const uint32_t ko = k * 32;
@@ -243,6 +267,34 @@ k_head(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUten
                     umma_commit(tfull(acc));                               // accumulator complete
                     if (++acc == 2) { acc = 0; aph ^= 1; }
                 }
+            }
+        }
+    } else if (INRING && (warp == 2 || warp == 3)) {
+        // ===================== converters: lo = x - trunc_tf32(x) of the freshly landed fp32 tiles =====================
+        const int ct = tid - 64;                                          // 0..63
+        int s = 0; uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            if (!head_tile_live(tile, a.Tb, a.B, a.T)) continue;
+            for (int it = 0; it < n_nt * n_kc; ++it) {
+                mbar_wait_or_trap(full(s), ph);
+                float4 *A4 = (float4 *)(sgen + (size_t)s * C::STAGE);
+                float4 *B4 = (float4 *)(sgen + (size_t)s * C::STAGE + 2 * H_A_BYTES);
+                auto lo_of = [](const float4 x) {
+                    float4 l;
+                    l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                    l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                    l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                    l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                    return l;
+                };
+#pragma unroll 4
+                for (int i = ct; i < (int)(H_A_BYTES / 16); i += 64) A4[H_A_BYTES / 16 + i] = lo_of(A4[i]);
+#pragma unroll 4
+                for (int i = ct; i < (int)(H_B_BYTES / 16); i += 64) B4[H_B_BYTES / 16 + i] = lo_of(B4[i]);
+                fence_proxy_async_smem_cta();                             // generic-proxy writes -> tcgen05.mma (async proxy) reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(conv(s));
+                if (++s == C::NSTAGE) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp >= 4) {

@@ -21,7 +21,7 @@ __attribute__((visibility("hidden"))) int internal_lattice(bool want_grad, const
 __attribute__((visibility("hidden"))) float internal_lin_thr(const Geom &g, int flags);
 __attribute__((visibility("hidden"))) float internal_occ_skip();
 __attribute__((visibility("hidden"))) int internal_sm_count(int *sms);
-// developer overrides of k_gemm3's MN-major operand description: 0 swizzle enum, 1 LBO, 2 SBO, 3 layout type (0 = default), 4 RNA split
+// developer overrides of k_gemm3's MN-major operand description: 0 swizzle enum, 1 LBO, 2 SBO, 3 layout type (0 = default), 4 RNA split, 5 k_head in-ring split
 __attribute__((visibility("hidden"))) int internal_g3_opt(int which);
 
 }  // namespace ctcb200

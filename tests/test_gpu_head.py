@@ -216,3 +216,20 @@ def test_param_grad_paths_agree():
             head._CFG_HEAD["param_grads"] = "tcgen05"
     for a, b in zip(res["tcgen05"], res["torch"]):
         assert (a - b).abs().max().item() <= 2e-5 * b.abs().max().item() + 1e-9   # cuBLAS fp32 itself is ~3e-6 off
+
+
+def test_in_ring_split_option_meets_the_same_bar():
+    """Option head_inring: k_head takes the raw fp32 tiles as the hi halves and splits in the shared-memory ring
+    (truncation split, as k_gemm3 does) instead of reading operands pre-split in HBM -- same parity bar."""
+    from asr_chinese_e2e_b200 import _lib
+    case = _case(3, 100, 64, 300, 7, 11, "var", False)
+    enc, W, b, tg, il, tl = case
+    try:
+        _lib.set_option("head_inring", 1)
+        loss, lu, fused, unfused, logits = _run(case, "3xtf32")
+    finally:
+        _lib.set_option("head_inring", 0)
+    rl, _ = ref_ctc(logits, tg, il, tl, reduction="mean", zero_infinity=True, want_grad=False)
+    assert abs(loss.item() - rl.item()) <= 1e-5 * abs(rl.item())
+    for f, u, name in zip(fused, unfused, ("d_enc", "d_weight", "d_bias")):
+        assert (f - u).abs().max().item() <= 1e-4 * u.abs().max().item() + 1e-9, name
