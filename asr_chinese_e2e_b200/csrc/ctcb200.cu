@@ -53,9 +53,11 @@ Opt g_opt[OPT_COUNT] = {
     // fused sweep: evict_last for the gradient chunks the sparse patch revisits.  Measured on B200 (round 2): the patch
     // still misses L2 (104 MB of DRAM reads either way) and the sweep gets 4 us slower -> off
     {"label_keep_l2", "CTCB200_LABEL_KEEP_L2", 0},
-    // 1: the alternative sweep kernel of round 2 (sweep_direct.cuh: aligned frame groups, direct LDG.128 loads into
-    // registers, one barrier per group, no shared-memory ring).  Measured on B200: the same speed as the TMA-ring
-    // kernel k1_lse_gather (C2 full lengths 0.618 vs 0.619 ms), so the ring kernel stays the default
+    // which sweep kernel: 0 = auto (k1p_sweep when frames pair up into 16-byte-aligned groups -- even V, even T --
+    // else k1_lse_gather), 1 = k1d_sweep (aligned groups, direct LDG.128 loads, 4 CTAs/SM: the same speed as
+    // k1_lse_gather, 0.618 vs 0.619 ms at C2 full lengths), 2 = k1p_sweep wherever it applies (aligned groups behind a
+    // bulk-TMA ring, 2 CTAs/SM, both frames of a group carried through the reductions interleaved: 0.587 vs 0.621 ms),
+    // 3 = k1_lse_gather (the round-1 kernel: one frame per ring slot, hull copies)
     {"sweep_direct", "CTCB200_SWEEP_DIRECT", 0},
     {"k1d_cps", "CTCB200_K1D_CPS", 0},                  // CTAs per SM of k1d_sweep (0 = 4, or 2 for wide vocabularies)
     // k_gemm3 (gemm_tf32x3.cuh), MN-major operand tiles: tensor-map swizzle enum, descriptor LBO / SBO (bytes) and layout
@@ -272,13 +274,45 @@ cudaError_t launch_k1d(cudaStream_t s, int sms, const K1dArgs &a) {
 // k1d_sweep launch; returns false (and launches nothing) when the shape does not fit
 template <bool FUSED>
 bool try_launch_k1d(cudaStream_t s, const DevInfo &dev, const K1dArgs &a, cudaError_t *err) {
-    if (a.P <= 0 || !opt(OPT_SWEEP_DIRECT) || a.Lp > 264) return false;
+    if (a.P <= 0 || opt(OPT_SWEEP_DIRECT) != 1 || a.Lp > 264) return false;
     if (((uintptr_t)a.logits & 15) || (FUSED && ((uintptr_t)a.grad & 15))) return false;
     const int nch = a.P * a.V / 4;
     if (nch <= 128 * 5) *err = launch_k1d<5, FUSED>(s, dev.sms, a);
     else if (nch <= 128 * 9) *err = launch_k1d<9, FUSED>(s, dev.sms, a);
     else if (nch <= 128 * 17) *err = launch_k1d<17, FUSED>(s, dev.sms, a);
     else if (nch <= 128 * 33) *err = launch_k1d<33, FUSED>(s, dev.sms, a);
+    else return false;
+    return true;
+}
+
+// k1p_sweep (sweep_direct = 2): the aligned-group sweep behind a bulk-TMA ring, two CTAs (= two frame streams) per SM
+template <int NT, int MAXC, bool FUSED>
+cudaError_t launch_k1p(cudaStream_t s, int sms, const K1dArgs &a) {
+    const uint32_t slot = (uint32_t)align_up((size_t)a.P * a.V * 4, 128);
+    const size_t fixed = 2 * (NT / 32) * 16 + 2 * (NT / 32) * 8 + 264 * 4 + 64;
+    int nst = opt_or(OPT_K1F_NST, 2);
+    if (nst > 8) nst = 8;
+    while (nst > 2 && 2 * ((size_t)nst * slot + 8 * nst + fixed + 1024) > kSmemBudget) --nst;
+    const size_t smem = (size_t)nst * slot + 8 * nst + fixed;
+    if (smem > kSmemBudget) return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(k1p_sweep<NT, MAXC, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    prefer_max_carveout(k1p_sweep<NT, MAXC, FUSED>);
+    const int cps = opt_or(OPT_K1D_CPS, 2);
+    return launch_pdl(0, k1p_sweep<NT, MAXC, FUSED>, dim3(sms * cps), dim3(NT), smem, s, a, nst, slot);
+}
+template <bool FUSED>
+bool try_launch_k1p(cudaStream_t s, const DevInfo &dev, const K1dArgs &a, cudaError_t *err) {
+    // auto (0): groups of two frames only -- that is where the instruction-level parallelism comes from; 2 forces it
+    const int mode = opt(OPT_SWEEP_DIRECT);
+    if (a.P <= 0 || !(mode == 2 || (mode == 0 && a.P == 2)) || a.Lp > 264) return false;
+    if (((uintptr_t)a.logits & 15) || (FUSED && ((uintptr_t)a.grad & 15))) return false;
+    const int nch = a.P * a.V / 4;
+    if ((size_t)a.P * a.V * 4 > 100 * 1024) return false;       // two stages of a group must fit
+    if (nch <= 128 * 5) *err = launch_k1p<128, 5, FUSED>(s, dev.sms, a);
+    else if (nch <= 128 * 9) *err = launch_k1p<128, 9, FUSED>(s, dev.sms, a);
+    else if (nch <= 128 * 17) *err = launch_k1p<128, 17, FUSED>(s, dev.sms, a);
+    else if (nch <= 128 * 33) *err = launch_k1p<128, 33, FUSED>(s, dev.sms, a);
     else return false;
     return true;
 }
@@ -357,6 +391,8 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
                             a.grad, a.reduction, a.inv_batch, a.best, a.zero_pad_here, slow, lin_thr, bad};
         if (fused ? try_launch_k1d<true>(s, dev, da, &e) : try_launch_k1d<false>(s, dev, da, &e)) {
             // the direct sweep was launched (or failed to launch: e)
+        } else if (fused ? try_launch_k1p<true>(s, dev, da, &e) : try_launch_k1p<false>(s, dev, da, &e)) {
+            // the ring-fed aligned-group sweep was launched
         } else if (fused) {
             if (nt1 == 64) e = STREAM_DISPATCH(launch_k1f, 64, rounds1, exact1, c, s, a);
             else e = STREAM_DISPATCH(launch_k1f, 128, rounds1, exact1, c, s, a);

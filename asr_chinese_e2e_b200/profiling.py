@@ -2,9 +2,9 @@
 
 ``time_stages``: one un-chunked ``ctcb200_loss_grad`` call on the current stream, bracketed by CUDA events on that
 stream; the library's own ``sweep_done`` event (recorded right after the fused sweep kernel) splits the
-call into  [k0_prep + k1_lse_gather<FUSED>]  and  [k2_lattice + k3p_patch].
+call into  [k0_prep + the fused sweep kernel]  and  [k2_lattice + k3p_patch].
 ``time_sweep_kernel``: the dominant kernel by itself -- the stage-split entry point launches k0_prep (stage 8) and the
-fused sweep (stage 16) separately with an event in between, so the timed interval holds k1_lse_gather<FUSED> alone.
+fused sweep (stage 16) separately with an event in between, so the timed interval holds the sweep kernel (k1p_sweep<FUSED>, or k1_lse_gather<FUSED> for odd V / T) alone.
 """
 from __future__ import annotations
 

@@ -13,7 +13,7 @@ One JSON line on stdout (rank 0):
   value         whole-job utterances/s with the logits resident in HBM (CUDA events, max over ranks)
   e2e           the same metric through the host-buffer API (pinned host logits in, gradient + nll back to pinned
                 host memory, copies inside the timed region)
-  roofline      the dominant kernel, k1_lse_gather<FUSED> (the fused sweep), timed live with CUDA events on the
+  roofline      the dominant kernel, the fused sweep (k1p_sweep<FUSED> at this shape), timed live with CUDA events on the
                 launching stream against the measured HBM peak; roofline_step = whole step
   parity        the step's nll / gradient against the CPU oracle (torch's CPU ctc_loss), checked in this very run
   cpu_baseline  torch's CPU log_softmax + ctc_loss + backward on the full batch (median; + a 1-thread figure)
@@ -527,7 +527,7 @@ def main():
     sweep_ms, rest_ms = statistics.mean(st["sweep_ms"]), statistics.mean(st["rest_ms"])
     k1_ms = time_sweep_kernel(x, tg, il, tl, reduction="mean", zero_infinity=False, iters=min(K, 50), warmup=3)
 
-    launches_per_step = 5                          # k0_prep, k1_lse_gather<FUSED>, k2_lattice, k3p_patch, k4_rescale (early exit)
+    launches_per_step = 5                          # k0_prep, k1p_sweep<FUSED>, k2_lattice, k3p_patch, k4_rescale (early exit)
     peak, peak_src = peaks()
     k1f_gbs = bytes_2sweep / (k1_ms / 1e3) / 1e9
     traffic = None
@@ -539,7 +539,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "b200",
             "config": workload_cfg(args, world), "loss": loss_val,
             "gpu_launches": launches_per_step * K,
-            "roofline": {"bound": "hbm", "kernel": "k1_lse_gather<FUSED> (log-softmax stats + label gather + dense gradient), "
+            "roofline": {"bound": "hbm", "kernel": "k1p_sweep<128,17,FUSED> (the fused sweep: log-softmax stats + label gather + dense gradient; aligned "
+                                                   "two-frame groups behind a bulk-TMA ring), "
                                                    "timed by itself: CUDA events around its launch on the launching stream "
                                                    "(stage-split ABI call: k0_prep | event | sweep | event)",
                          "achieved": k1f_gbs, "peak": peak, "unit": "GB/s", "frac": k1f_gbs / peak, "traffic": traffic,

@@ -403,13 +403,16 @@ def test_skipping_negligible_occupancies_changes_nothing_measurable():
     assert diff <= 2.0 ** -39                                   # occupancy + at most half an ulp of the result
 
 
-def test_direct_sweep_option_is_parity_green():
-    """The alternative sweep kernel (sweep_direct.cuh: aligned frame groups, direct loads, one barrier per group) behind
-    the `sweep_direct` option: same parity suite, including an odd last frame, infeasible utterances, the non-fused
-    paths and V % 4 == 0; shapes it does not cover (odd V, odd T) silently use the ring kernel."""
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_direct_sweep_option_is_parity_green(variant):
+    """Every sweep kernel behind the `sweep_direct` option (1: k1d_sweep, aligned frame groups, direct loads, one barrier
+    per group; 2: k1p_sweep, the same groups fed by a bulk-TMA ring, two CTAs per SM -- what 0 = auto picks for even V
+    and T; 3: k1_lse_gather, one frame per ring slot): same parity suite, including an odd last frame, infeasible
+    utterances, the non-fused paths and V % 4 == 0; shapes the group kernels do not cover (odd V, odd T) silently use
+    k1_lse_gather."""
     from asr_chinese_e2e_b200 import _lib
     try:
-        _lib.set_option("sweep_direct", 1)
+        _lib.set_option("sweep_direct", variant)
         for (B, T, V, U, seed) in ((7, 62, 54, 13, 21), (5, 40, 64, 7, 22), (3, 200, 4234, 30, 23), (4, 31, 53, 6, 24)):
             c = make_case(B, T, V, U, seed, dist="D2", n_infeasible=1, n_partial=1)
             c["input_lengths"][0] = T - 1 if T % 2 == 0 else T            # an odd number of valid frames
