@@ -1,19 +1,15 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -q --tb=short -p no:cacheprovider -x > gpurun_out/c21_pytest.log 2>&1
+tail -3 gpurun_out/c21_pytest.log
 run() { env "$@" timeout 200 python bench.py $P 2>> gpurun_out/c21.err | python -c "
 import sys,json
 d=json.loads(sys.stdin.read()); print('$*', 'k1 ms', round(d['roofline']['ms_per_launch'],4), 'step', round(d['ms_per_step'],4), d.get('parity',{}).get('pass'))"; }
 P="--steps 100 --warmup 5 --no-e2e --no-cpu --no-configs --lengths full"
+run CTCB200_SWEEP_DIRECT=3
 run CTCB200_SWEEP_DIRECT=0
-run CTCB200_SWEEP_DIRECT=2
-run CTCB200_SWEEP_DIRECT=2 CTCB200_K1F_NST=3
-run CTCB200_SWEEP_DIRECT=2 CTCB200_K1F_NT=256
-run CTCB200_SWEEP_DIRECT=2 CTCB200_K1F_NT=256 CTCB200_K1F_NST=3
-run CTCB200_SWEEP_DIRECT=2 CTCB200_K1F_NT=256 CTCB200_K1D_CPS=1 CTCB200_K1F_NST=4
-run CTCB200_SWEEP_DIRECT=2 CTCB200_K1F_NT=256 CTCB200_K1D_CPS=3
 P="--steps 100 --warmup 5 --no-e2e --no-cpu --no-configs"
+run CTCB200_SWEEP_DIRECT=3
 run CTCB200_SWEEP_DIRECT=0
-run CTCB200_SWEEP_DIRECT=2
-run CTCB200_SWEEP_DIRECT=2 CTCB200_K1F_NT=256
 tail -3 gpurun_out/c21.err
