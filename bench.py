@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--no-configs", action="store_true", help="skip the C2-full / C2-D2 / C4 / C5 sub-records")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--same-seed", action="store_true", help="N>1 experiment: every rank gets rank 0's batch")
+    ap.add_argument("--per-rank-lengths", action="store_true",
+                    help="N>1: every rank also draws its own lengths / transcripts (per-GPU work then varies with the "
+                         "rank; default: rank 0's lengths and transcripts on every rank, each rank its own logits)")
     ap.add_argument("--vocab", type=int, default=V_, help="developer experiments only (default = BASELINE V)")
     ap.add_argument("--shape", default=None, help="developer experiments only: B,T,U (default = BASELINE C2 256,400,50)")
     return ap.parse_args()
@@ -210,6 +213,9 @@ def workload_cfg(args, n):
                         f"{'variable lengths ~U[T/2,T] with padding' if args.lengths == 'var' else 'full lengths'}, "
                         "reduction=mean, zero_infinity=False, randn logits (D1)",
             "global_batch": B_ * n, "lengths": args.lengths, "seed": SEED,
+            "per_rank_data": ("n/a" if n == 1 else "rank 0's batch on every rank" if args.same_seed else
+                              "own logits, lengths and transcripts per rank" if args.per_rank_lengths else
+                              "own logits per rank; rank 0's lengths and transcripts (fixed work per GPU)"),
             "parallelism": f"batch-sharded x{n}, 1 all-reduce of 1 float/step" if n > 1 else "single GPU",
             "l2_policy": "inputs (1.73 GB logits + 1.73 GB grad per step) exceed the 126 MB L2; no flush needed"}
 
@@ -472,6 +478,14 @@ def main():
     dev = torch.device("cuda", local)
 
     c = make_batch(0 if args.same_seed else rank, args.lengths)
+    if world > 1 and rank > 0 and not args.same_seed and not args.per_rank_lengths:
+        # weak scaling = FIXED work per GPU as N grows: every rank sweeps its own logits, but with rank 0's lengths and
+        # transcripts, so that sum(T_b) -- the bytes a rank moves -- does not depend on the rank (with per-rank lengths
+        # the step is as slow as the rank that happened to draw the longest utterances: +14 us at N = 8)
+        c0 = make_batch(0, args.lengths)
+        for key in ("targets", "input_lengths", "target_lengths"):
+            c[key] = c0[key]
+        del c0
     x = c["logits"].to(dev).requires_grad_(True)
     tg, il, tl = c["targets"].to(dev), c["input_lengths"].to(dev), c["target_lengths"].to(dev)
     sum_T = int(c["input_lengths"].sum())
@@ -602,7 +616,8 @@ def main():
                         "slowest_rank_us": 1e3 * float(tmax[0] - tmin[0]),
                         "note": "comm_us = step with the all-reduce minus the same step without it (max over ranks); "
                                 "slowest_rank_us = spread of the collective-free step across ranks (each rank draws its "
-                                "own lengths unless --same-seed)", "same_seed": bool(args.same_seed)}
+                                "own lengths only with --per-rank-lengths)", "same_seed": bool(args.same_seed),
+                        "per_rank_lengths": bool(args.per_rank_lengths)}
 
     if not args.no_e2e:
         e = run_e2e(torch, c, args, dev)

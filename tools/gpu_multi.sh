@@ -9,6 +9,6 @@ if [ "$N" = "2" ]; then
 fi
 timeout 900 $TR bench.py --gpus $N --steps 200 --warmup 10 > gpurun_out/m${N}_bench.json 2> gpurun_out/m${N}_bench.err
 echo "rc $?" >> gpurun_out/m${N}_bench.err
-timeout 600 $TR bench.py --gpus $N --steps 200 --warmup 10 --same-seed --no-e2e --no-configs > gpurun_out/m${N}_bench_sameseed.json 2> gpurun_out/m${N}_sameseed.err
-echo "rc $?" >> gpurun_out/m${N}_sameseed.err
+timeout 600 $TR bench.py --gpus $N --steps 200 --warmup 10 --per-rank-lengths --no-e2e --no-configs > gpurun_out/m${N}_bench_perrank.json 2> gpurun_out/m${N}_perrank.err
+echo "rc $?" >> gpurun_out/m${N}_perrank.err
 echo done
