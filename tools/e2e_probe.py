@@ -39,15 +39,12 @@ def run(label, **kw):
     print(f"{label}: {1e3 * (time.perf_counter() - t0) / 8:.2f} ms/step  h2d {pipe.h2d_bytes / 1e9:.3f} GB d2h {pipe.d2h_bytes / 1e9:.3f} GB", flush=True)
 
 
-run("all frames, staged logits, chunk 32", valid_frames_only=False, zero_copy_logits=False)
-run("valid frames, staged logits, chunk 32", zero_copy_logits=False)
-run("valid frames, staged logits, no host zeroing (floor)", nozero=True, zero_copy_logits=False)
-run("all frames back, zero-copy logits, chunk 32", valid_frames_only=False)
-for ch in (8, 16, 32, 64):
-    run(f"valid frames, zero-copy logits, chunk {ch}", chunk=ch)
-run("valid frames, zero-copy logits, chunk 16, no host zeroing (floor)", chunk=16, nozero=True)
-run("valid frames, zero-copy logits, chunk 16, 4 slots", chunk=16, n_slots=4)
-run("valid frames, zero-copy, grad on device", grad_to_host=False)
+run("all frames, chunk 32", valid_frames_only=False)
+run("all frames, chunk 16", valid_frames_only=False, chunk=16)
+for ch, ns in ((4, 3), (8, 3), (8, 6), (16, 3), (16, 4), (16, 6), (32, 3), (32, 4)):
+    run(f"valid frames, chunk {ch}, {ns} slots", chunk=ch, n_slots=ns)
+run("valid frames, chunk 16, no host zeroing (floor)", chunk=16, nozero=True)
+run("valid frames, grad on device, chunk 16", grad_to_host=False, chunk=16)
 # raw host fill bandwidth on this box
 import numpy as np
 a = h_g.numpy()

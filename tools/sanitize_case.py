@@ -5,7 +5,9 @@ import torch
 from asr_chinese_e2e_b200 import ctc_loss_b200
 from oracle.synth import make_case
 
-for (B, T, V, U, kw) in [(5, 23, 37, 6, {}), (3, 17, 4234, 9, {}), (4, 160, 131, 70, {}), (3, 290, 67, 130, {})]:
+# odd V / T -> k1_lse_gather; even V and T -> k1p_sweep (groups of two frames, incl. an odd number of valid frames)
+for (B, T, V, U, kw) in [(5, 23, 37, 6, {}), (3, 17, 4234, 9, {}), (4, 160, 131, 70, {}), (3, 290, 67, 130, {}),
+                         (5, 24, 38, 6, {}), (3, 18, 4234, 9, {}), (4, 160, 130, 70, {}), (2, 40, 64, 7, {})]:
     c = make_case(B, T, V, U, 11, dist="D2", n_infeasible=1)
     for fused in (True, False):
         x = c["logits"].cuda().requires_grad_(True)
