@@ -109,6 +109,17 @@ __device__ __forceinline__ void stg_f32_hint(float *p, float v, uint64_t policy)
 __device__ __forceinline__ void fence_proxy_async_global() {
     asm volatile("fence.proxy.async.global;" ::: "memory");
 }
+// 1-D bulk TMA store shared -> global (bulk async-group completion), with an L2 policy; dst/src 16-byte aligned
+__device__ __forceinline__ void tma_store_1d_hint(void *dst, uint32_t src, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(dst), "r"(src), "r"(bytes), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups have not yet READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 // generic-proxy writes to shared memory -> later async-proxy reads of the same bytes (tcgen05.mma operands, bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem_cta() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

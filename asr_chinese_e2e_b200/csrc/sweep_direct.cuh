@@ -232,7 +232,12 @@ __global__ void __launch_bounds__(128, (MAXC <= 17 ? 4 : 2)) k1d_sweep(const K1d
 // So: keep TWO streams per SM, and get the latency hiding from instruction-level parallelism instead of occupancy --
 // a ring slot holds a whole aligned group (two adjacent frames, one 33 872-byte bulk copy, no hull, no edge threads),
 // every thread carries both frames through max / exp / sum interleaved, and one barrier serves the group.
-template <int NT, int MAXC, bool FUSED>
+// BULKST (FUSED only): the gradient of a group does not leave through 17 STG.128 per thread but goes back into the
+// group's ring slot (in place) and is written to global memory by ONE bulk-TMA store (cp.async.bulk.global.shared)
+// issued by thread 0 after a second block barrier; a slot is refilled one group later, once its store has read it
+// (cp.async.bulk.wait_group.read), so the ring needs three slots: one landing, one being computed, one leaving.  A
+// padded odd frame is written as zeros (what zero_padded_frames writes there as well).
+template <int NT, int MAXC, bool FUSED, bool BULKST = false>
 __global__ void __launch_bounds__(NT, 2) k1p_sweep(const K1dArgs a, const int nst, const uint32_t slot_bytes) {
     constexpr int NW = NT / 32;
     extern __shared__ __align__(128) unsigned char smem_p[];
@@ -387,7 +392,8 @@ __global__ void __launch_bounds__(NT, 2) k1p_sweep(const K1dArgs a, const int ns
         s0 = warp_sum(s0); s1 = warp_sum(s1);
         if (lane == 0) { rd[0] = mw0; rd[1] = mw1; rd[2] = s0; rd[3] = s1; }
         __syncthreads();                     // the group's only barrier: partials visible, slot consumed
-        if (tid == 0 && issued < ng) issue(stage);               // refill the slot with group i + nst
+        const int cur_stage = stage;
+        if (!(BULKST && FUSED) && tid == 0 && issued < ng) issue(stage);   // refill the slot with group i + nst
         if (++stage == nst) { stage = 0; parity ^= 1; }
         float M0 = CTC_NEG_INF, M1 = CTC_NEG_INF;
 #pragma unroll
@@ -432,6 +438,27 @@ __global__ void __launch_bounds__(NT, 2) k1p_sweep(const K1dArgs a, const int ns
             const float f0 = gsc * ex2f(e0 - M0l) * __frcp_rn(S0);
             const float f1 = live1 ? gsc * ex2f(e1 - M1l) * __frcp_rn(S1) : 0.f;   // a padded odd frame gets its zeros here
             float4 *o4 = (float4 *)(a.grad + ((size_t)b * T + t0) * V);
+            if (BULKST) {
+                float4 *w4 = (float4 *)(smem_p + (size_t)cur_stage * slot_bytes);   // in place: this group's own slot
+#pragma unroll
+                for (int k = 0; k < MAXC; ++k) {
+                    const int c = tid + k * NT;
+                    if (c < nch) {
+                        const float fa = c <= mid ? f0 : f1, fb = c < mid ? f0 : f1;     // (f1 = 0 for a padded odd frame)
+                        w4[c] = make_float4(v[k].x * fa, v[k].y * fa, v[k].z * fb, v[k].w * fb);
+                    }
+                }
+                fence_proxy_async_smem_cta();                    // these writes -> the bulk store's (async proxy) reads
+                __syncthreads();                                 // second barrier of the group: the slot is complete
+                if (tid == 0) {
+                    tma_store_1d_hint(o4, slot0 + cur_stage * slot_bytes, group_bytes, kEvictFirst);
+                    bulk_commit_group();
+                    if (i >= 1 && issued < ng) {                 // slot of group i-1: its store has read it by now
+                        bulk_wait_group_read<1>();
+                        issue(issued % nst);
+                    }
+                }
+            } else {
 #pragma unroll
             for (int k = 0; k < MAXC; ++k) {
                 const int c = tid + k * NT;
@@ -442,6 +469,7 @@ __global__ void __launch_bounds__(NT, 2) k1p_sweep(const K1dArgs a, const int ns
                                                   hi_live ? v[k].w * fb : 0.f));
                 }
             }
+            }
         }
         if (++j >= ngb) {                    // next group
             j = 0;
@@ -449,7 +477,7 @@ __global__ void __launch_bounds__(NT, 2) k1p_sweep(const K1dArgs a, const int ns
             if (b < B) ngb = a.gstart[b + 1] - a.gstart[b];
         }
     }
+    if (BULKST && FUSED && tid == 0) bulk_wait_group<0>();      // shared memory must outlive the bulk stores
 }
-
 
 }  // namespace ctcb200

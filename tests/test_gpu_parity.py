@@ -403,7 +403,7 @@ def test_skipping_negligible_occupancies_changes_nothing_measurable():
     assert diff <= 2.0 ** -39                                   # occupancy + at most half an ulp of the result
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 12, 3])
 def test_direct_sweep_option_is_parity_green(variant):
     """Every sweep kernel behind the `sweep_direct` option (1: k1d_sweep, aligned frame groups, direct loads, one barrier
     per group; 2: k1p_sweep, the same groups fed by a bulk-TMA ring, two CTAs per SM -- what 0 = auto picks for even V
@@ -412,7 +412,8 @@ def test_direct_sweep_option_is_parity_green(variant):
     k1_lse_gather."""
     from asr_chinese_e2e_b200 import _lib
     try:
-        _lib.set_option("sweep_direct", variant)
+        _lib.set_option("sweep_direct", variant % 10)
+        _lib.set_option("k1p_bulkst", 0 if variant == 12 else 1)     # 12: k1p_sweep with per-thread STG.128 stores
         for (B, T, V, U, seed) in ((7, 62, 54, 13, 21), (5, 40, 64, 7, 22), (3, 200, 4234, 30, 23), (4, 31, 53, 6, 24)):
             c = make_case(B, T, V, U, seed, dist="D2", n_infeasible=1, n_partial=1)
             c["input_lengths"][0] = T - 1 if T % 2 == 0 else T            # an odd number of valid frames
@@ -428,3 +429,4 @@ def test_direct_sweep_option_is_parity_green(variant):
             assert info["hyp"][b, : int(info["hyp_len"][b])].tolist() == want[b]
     finally:
         _lib.set_option("sweep_direct", 0)
+        _lib.set_option("k1p_bulkst", 1)
