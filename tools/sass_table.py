@@ -30,7 +30,7 @@ for k, c in counts.items():
     rows.append((name, c))
 # one representative instantiation per family: the ones the C2 / C4 configurations launch
 KEEP = [r"^k0_prep", r"^k4_rescale", r"^k1_lse_gather<128, 9, true, true, false>", r"^k1_lse_gather<64, 17, true, false, false>",
-        r"^k1d_sweep<17, true>", r"^k2_lattice<(4|8), (true|false)>", r"^k3_grad<128, 9, true>", r"^k3p_patch", r"^k5_greedy_cer<4>",
+        r"^k1d_sweep<17, true>", r"^k1p_sweep<128, 17, true, (true|false)>", r"^k2_lattice<(4|8), (true|false)>", r"^k3_grad<128, 9, true>", r"^k3p_patch", r"^k5_greedy_cer<4>",
         r"^kce_rows<128, 9, true", r"^k_head", r"^k_gemm3", r"^k_split_tf32", r"^k_sum_partials", r"^k6_edit"]
 rows = [r for r in rows if any(re.search(k, r[0]) for k in KEEP)]
 for name, c in sorted(rows):
@@ -39,7 +39,7 @@ print("""
 `UTCHMMA` = `tcgen05.mma` (kind::tf32: the fused CTC head `k_head` and the parameter-gradient GEMM `k_gemm3`), `UTMALDG` = tensor-map
 TMA loads (`cp.async.bulk.tensor.2d`), `LDTM` = `tcgen05.ld` (TMEM -> registers in the epilogues), `UTCBAR` = `tcgen05.commit`,
 `USETMAXREG` = `setmaxnreg` (k_gemm3 moves registers from the producer warpgroup to the epilogue warpgroups),
-`UBLKCP` = 1-D bulk TMA copy (`cp.async.bulk`: logits rows of non-16-byte-multiple pitch), `SYNCS` = mbarrier operations,
+`UBLKCP` = 1-D bulk TMA copy (`cp.async.bulk`: logits frame groups in, and in `k1p_sweep<..,BULKST>` gradient groups out), `SYNCS` = mbarrier operations,
 `REDG` = reductions to global memory (the sparse occupancy corrections of `k3p_patch`; the few in the sweep kernels are the
 status-word `atomicOr`).  The lattice kernel holds both recursions (float64 `DFMA/DMUL/DADD` fast path, `MUFU` log-space fallback).
 Tensor-core instructions appear only in the two GEMM-shaped kernels of section 8f-1; the core CTC path is HBM- and latency-bound.""")
