@@ -309,7 +309,8 @@ template <bool FUSED>
 bool try_launch_k1p(cudaStream_t s, const DevInfo &dev, const K1dArgs &a, cudaError_t *err) {
     // auto (0): groups of two frames only -- that is where the instruction-level parallelism comes from; 2 forces it
     const int mode = opt(OPT_SWEEP_DIRECT);
-    if (a.P <= 0 || !(mode == 2 || (mode == 0 && a.P == 2)) || a.Lp > 264) return false;
+    // (auto also wants the group to fit 17 chunks per thread: two CTAs per SM with three ring slots each)
+    if (a.P <= 0 || !(mode == 2 || (mode == 0 && a.P == 2 && a.P * a.V / 4 <= 128 * 17)) || a.Lp > 264) return false;
     if (((uintptr_t)a.logits & 15) || (FUSED && ((uintptr_t)a.grad & 15))) return false;
     const int nch = a.P * a.V / 4;
     if ((size_t)a.P * a.V * 4 > 100 * 1024) return false;       // two stages of a group must fit
