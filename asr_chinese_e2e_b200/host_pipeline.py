@@ -70,6 +70,24 @@ class HostCTCPipeline:
         self.d2h_bytes = (B * T * V * 4 if grad_to_host else 0) + B * 4
         self.launches_per_step = 4 * ((B + self.chunk - 1) // self.chunk)
 
+    def close(self):
+        """Stops the host threads that zero the padded gradient rows (idempotent)."""
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     @staticmethod
     def _runs(lens, lo, hi, T):
         """Utterances [lo, hi) as (first, end, frames) copy operations: a run of full-length utterances is contiguous
@@ -173,8 +191,11 @@ class HostCTCPipeline:
                     # the padded rows of the host buffer: zeros written by host threads (disjoint from the rows the DMA
                     # writes) while the copies are in flight
                     step = max(1, (n + 3) // 4)
-                    for b0 in range(lo, hi, step):
-                        pending.append(self._pool.submit(zero_padded, b0, min(b0 + step, hi)))
+                    if self._pool is None:                           # (closed pipeline reused: zero inline)
+                        zero_padded(lo, hi)
+                    else:
+                        for b0 in range(lo, hi, step):
+                            pending.append(self._pool.submit(zero_padded, b0, min(b0 + step, hi)))
         self.h2d_bytes, self.d2h_bytes = h2d, d2h
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_stream(self.s_cmp)

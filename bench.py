@@ -704,6 +704,7 @@ def run_e2e(torch, c, args, dev, grad_to_host=True, valid_frames_only=True):
     ms = 1e3 * (time.perf_counter() - t0) / k
     loss = float((h_n / h_tl.clamp(min=1).float()).mean())
     h2d, d2h, launches = pipe.h2d_bytes, pipe.d2h_bytes, pipe.launches_per_step
+    pipe.close()
     del pipe
     torch.cuda.empty_cache()
     return {"value": B_ / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
