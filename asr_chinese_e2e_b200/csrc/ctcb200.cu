@@ -30,7 +30,7 @@ enum OptId {
     OPT_PDL, OPT_LATTICE_LOG, OPT_LIN_THR, OPT_K1F_NT, OPT_K1F_NST, OPT_K1F_CPS, OPT_K1_NT, OPT_K1_NST, OPT_K1_CPS,
     OPT_K3_NT, OPT_K3_NST, OPT_K3_CPS, OPT_CE_NST, OPT_CE_CPS, OPT_K3P_CPS, OPT_OCC_SKIP_BITS,
     OPT_ZERO_IN_LATTICE, OPT_ZERO_CPS, OPT_SKIP_LATTICE, OPT_LABEL_KEEP_L2, OPT_SWEEP_DIRECT, OPT_K1D_CPS,
-    OPT_G3_SWZ, OPT_G3_LBO, OPT_G3_SBO, OPT_G3_LAYOUT, OPT_G3_RNA_SPLIT, OPT_HEAD_INRING, OPT_SCRATCH_POLICY, OPT_K1P_BULKST, OPT_COUNT
+    OPT_G3_SWZ, OPT_G3_LBO, OPT_G3_SBO, OPT_G3_LAYOUT, OPT_G3_RNA_SPLIT, OPT_HEAD_INRING, OPT_SCRATCH_POLICY, OPT_K1P_BULKST, OPT_K1P_STORE_POLICY, OPT_COUNT
 };
 struct Opt { const char *name, *env; int value; };
 Opt g_opt[OPT_COUNT] = {
@@ -77,6 +77,7 @@ Opt g_opt[OPT_COUNT] = {
     // k1p_sweep: 1 (default) = the gradient of a group goes back into its ring slot and leaves through ONE bulk-TMA
     // store (cp.async.bulk.global.shared) instead of 17 STG.128 per thread: 0.586 -> 0.572 ms (C2 full), 0.5195 -> 0.507
     {"k1p_bulkst", "CTCB200_K1P_BULKST", 1},
+    {"k1p_store_policy", "CTCB200_K1P_STORE_POLICY", 0},  // L2 policy of those bulk stores: 0 evict_first, 1 normal, 2 evict_last
 };
 const bool g_opt_loaded = [] {
     for (Opt &o : g_opt) {
@@ -97,6 +98,18 @@ int apply_scratch_policy(cudaStream_t s) {
     cudaError_t e = cudaMemcpyToSymbolAsync(c_scratch_policy, &pol, sizeof(pol), 0, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return (int)e;
     e = cudaStreamSynchronize(s);                               // `pol` is a stack variable
+    if (e != cudaSuccess) return (int)e;
+    applied = want;
+    return 0;
+}
+int apply_gstore_policy(cudaStream_t s) {
+    static int applied = 0;
+    const int want = opt(OPT_K1P_STORE_POLICY);
+    if (want == applied) return 0;
+    const uint64_t pol = want == 1 ? kEvictNormal : (want == 2 ? kEvictLast : kEvictFirst);
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_gstore_policy, &pol, sizeof(pol), 0, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return (int)e;
     applied = want;
     return 0;
@@ -346,7 +359,7 @@ int forward_impl(bool want_grad, const FusedGrad *fg, const float *logits, const
     DevInfo dev;
     if ((rc = device_info(&dev))) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    if ((rc = apply_scratch_policy(s))) return rc;
+    if ((rc = apply_scratch_policy(s)) || (rc = apply_gstore_policy(s))) return rc;
     unsigned char *ws = (unsigned char *)workspace;
     int *hdr = (int *)(ws + w.hdr);
     int *Tb = (int *)(ws + w.Tb), *Ub = (int *)(ws + w.Ub), *flags = (int *)(ws + w.flags);

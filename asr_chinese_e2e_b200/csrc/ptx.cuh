@@ -76,6 +76,8 @@ constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 // translation unit, only ctcb200.cu's copy is ever changed or used.
 static __constant__ uint64_t c_scratch_policy = kEvictLast;
 #define kScratch c_scratch_policy
+// L2 policy of k1p_sweep's bulk gradient stores (option k1p_store_policy: 0 evict_first, 1 evict_normal, 2 evict_last)
+static __constant__ uint64_t c_gstore_policy = kEvictFirst;
 
 __device__ __forceinline__ void tma_load_1d_hint(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar,
                                                  uint64_t policy) {

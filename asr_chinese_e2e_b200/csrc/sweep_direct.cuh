@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(NT, 2) k1p_sweep(const K1dArgs a, const int ns
                 fence_proxy_async_smem_cta();                    // these writes -> the bulk store's (async proxy) reads
                 __syncthreads();                                 // second barrier of the group: the slot is complete
                 if (tid == 0) {
-                    tma_store_1d_hint(o4, slot0 + cur_stage * slot_bytes, group_bytes, kEvictFirst);
+                    tma_store_1d_hint(o4, slot0 + cur_stage * slot_bytes, group_bytes, c_gstore_policy);
                     bulk_commit_group();
                     if (i >= 1 && issued < ng) {                 // slot of group i-1: its store has read it by now
                         bulk_wait_group_read<1>();

@@ -1,15 +1,14 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-CTCB200_K1P_BULKST=2 timeout 300 python -m pytest tests/test_gpu_fullsize.py tests/test_gpu_parity.py -q --tb=short -p no:cacheprovider -x -k "not direct_sweep" > gpurun_out/c21_pytest.log 2>&1
-tail -2 gpurun_out/c21_pytest.log
 run() { env "$@" timeout 200 python bench.py $P 2>> gpurun_out/c21.err | python -c "
 import sys,json
 d=json.loads(sys.stdin.read()); print('$*', 'k1 ms', round(d['roofline']['ms_per_launch'],4), 'frac', round(d['roofline']['frac'],4), 'step', round(d['ms_per_step'],4), d.get('parity',{}).get('pass'))"; }
 P="--steps 100 --warmup 5 --no-e2e --no-cpu --no-configs --lengths full"
-run CTCB200_K1P_BULKST=1
-run CTCB200_K1P_BULKST=2
+run CTCB200_K1P_STORE_POLICY=0
+run CTCB200_K1P_STORE_POLICY=1
+run CTCB200_K1P_STORE_POLICY=2
 P="--steps 100 --warmup 5 --no-e2e --no-cpu --no-configs"
-run CTCB200_K1P_BULKST=1
-run CTCB200_K1P_BULKST=2
+run CTCB200_K1P_STORE_POLICY=0
+run CTCB200_K1P_STORE_POLICY=1
 tail -3 gpurun_out/c21.err
