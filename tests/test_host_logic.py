@@ -144,3 +144,22 @@ def test_mixin_under_the_real_reference_model(monkeypatch):
     # padded encoder frames are zeroed by the reference encoder => ctc logits there equal the bias
     out = m.forward(batch)
     assert torch.allclose(out.ctc_logits[2, 11:], m.ctc_head.bias.expand(T - 11, -1), atol=1e-6)
+
+
+def test_host_pipeline_copy_plan_covers_exactly_the_valid_frames():
+    """HostCTCPipeline._runs (host logic of the valid-frames-only transfers): a run of full-length utterances is one
+    copy, every shorter utterance a copy of its own first frames, zero-length utterances copy nothing -- and the plan
+    covers every valid frame of the chunk exactly once."""
+    from asr_chinese_e2e_b200.host_pipeline import HostCTCPipeline
+    T = 40
+    lens = [40, 40, 17, 0, 40, 40, 40, 25, 40, 3]
+    plan = list(HostCTCPipeline._runs(lens, 0, len(lens), T))
+    assert plan == [(0, 2, 40), (2, 3, 17), (3, 4, 0), (4, 7, 40), (7, 8, 25), (8, 9, 40), (9, 10, 3)]
+    covered = [0] * len(lens)
+    for b0, b1, nt in plan:
+        for b in range(b0, b1):
+            covered[b] += nt
+    assert covered == lens
+    # chunk boundaries cut runs: no copy ever spans two chunks
+    assert list(HostCTCPipeline._runs(lens, 4, 6, T)) == [(4, 6, 40)]
+    assert list(HostCTCPipeline._runs(lens, 1, 3, T)) == [(1, 2, 40), (2, 3, 17)]
