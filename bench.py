@@ -553,8 +553,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "b200",
             "config": workload_cfg(args, world), "loss": loss_val,
             "gpu_launches": launches_per_step * K,
-            "roofline": {"bound": "hbm", "kernel": "k1p_sweep<128,17,FUSED> (the fused sweep: log-softmax stats + label gather + dense gradient; aligned "
-                                                   "two-frame groups behind a bulk-TMA ring), "
+            "roofline": {"bound": "hbm", "kernel": "k1p_sweep<128,17,FUSED,BULKST> (the fused sweep: log-softmax stats + label gather + dense "
+                                                   "gradient; aligned two-frame groups through a bulk-TMA ring, in and out), "
                                                    "timed by itself: CUDA events around its launch on the launching stream "
                                                    "(stage-split ABI call: k0_prep | event | sweep | event)",
                          "achieved": k1f_gbs, "peak": peak, "unit": "GB/s", "frac": k1f_gbs / peak, "traffic": traffic,
